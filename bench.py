@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Benchmark of the eigen-pinns hot path on B200: training steps per second of the corrector on the
+eigen-loss (BASELINE.json metric "train steps/s at 1M/16M verts, k=32 eigs").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one epoch body of the reference loop (src/multigrid_model.py:237-261) on the whole mesh:
+corrector forward, U_pred, K U / M U, Rayleigh / residual / Gram terms, analytic backward, MLP
+backward, clip + Adam.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the roofline
+arithmetic used below.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+SRC = os.path.join(ROOT, "eigen-pinns_b200", "src")
+
+WORKLOADS = {
+    # name: (kind, size parameter, k)
+    "icosphere1m": ("icosphere", 316, 32),      # 998,562 vertices, BASELINE config 4
+    "icosphere100k": ("icosphere", 100, 32),    # bounded CPU sample of the same workload
+    "icosphere10k": ("icosphere", 32, 32),
+    "torus16m": ("torus", 4096, 64),            # 16,777,216 vertices, BASELINE config 5
+    "torus1m": ("torus", 1024, 64),
+}
+HIDDEN = [256] * 6                               # reference default (src/parameters.yml)
+
+
+def pkg(name=None):
+    return importlib.import_module("eigen-pinns_b200" + ("." + name if name else ""))
+
+
+def mlp_flops_per_vertex(d_in, hidden, k):
+    """fwd 2S + bwd (4S - 2*d_in*h0): no input-gradient GEMM for the first layer."""
+    dims = [d_in] + list(hidden) + [k]
+    S = sum(dims[i] * dims[i + 1] for i in range(len(dims) - 1))
+    return 6 * S - 2 * dims[0] * dims[1]
+
+
+def build_host_workload(name):
+    """Synthetic mesh, FEM operators, initial subspace and node features on the host (float64 / numpy)."""
+    kind, size, k = WORKLOADS[name]
+    fem, syn = pkg("fem"), pkg("synthetic")
+    rng = np.random.default_rng(0)
+    if kind == "icosphere":
+        verts, tris = syn.icosphere(size)
+        unit = verts.copy()
+        verts = fem.normalize_verts(verts)
+        modes, degs = syn.real_spherical_harmonics(unit, k)
+        radius2 = float((verts ** 2).sum(1).mean())
+        lam_analytic = degs * (degs + 1) / (2.0 * radius2)     # reference mass matrix is 2x the lumped area
+    else:
+        verts, tris = syn.torus(size, size)
+        verts = fem.normalize_verts(verts)
+        modes, lam_analytic = syn.torus_trial_modes(size, size, k), None
+    K, M = fem.assemble_stiffness_mass(verts, tris)
+    edges = fem.connectivity_edges(tris)
+    U0 = (modes + 0.05 * rng.standard_normal(modes.shape)).astype(np.float32)
+    return dict(name=name, k=k, verts=verts, tris=tris, K=K, M=M, edges=edges, U0=U0, modes=modes,
+                lam_analytic=lam_analytic)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5),
+                              ("sw_power_cap", 6)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], bf16_burst=p["bf16_tflops"], bf16_sustained=p.get("bf16_tflops_sustained",
+                    p["bf16_tflops"]), source="measured")
+    return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_reference_steps_per_s(sample_name, full_vertices, steps, warmup, threads=None):
+    """Time the CPU oracle (torch-CPU port of the reference step, oracle/step_port.py) on a bounded sample
+    of the workload and scale to the full vertex count (the step is linear in the number of vertices)."""
+    import torch
+    from oracle import step_port
+    if threads:
+        torch.set_num_threads(threads)
+    w = build_host_workload(sample_name)
+    n, k = w["verts"].shape[0], w["k"]
+    U_base = step_port.m_normalize(torch.from_numpy(w["U0"]), w["M"])
+    ei = torch.from_numpy(w["edges"])
+    lam = torch.zeros(k)
+    x = step_port.level_features(w["verts"], U_base, torch.linspace(0, 1, k), ei, w["K"], w["M"], 0, 1)
+    tr = step_port.CorrectorTrainer(x, ei, U_base, [w["K"]], [w["M"]], lam, HIDDEN, k)
+    tr.epoch = 2500
+    for _ in range(warmup):
+        tr.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.step()
+    dt = (time.perf_counter() - t0) / steps
+    scale = full_vertices / n
+    return dict(sample_ms=dt * 1e3, sample_vertices=n, ms_per_step=dt * 1e3 * scale, steps_per_s=1.0 / (dt * scale),
+                threads=torch.get_num_threads())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kind, size, k = WORKLOADS[args.workload]
+    full_n = 10 * size * size + 2 if kind == "icosphere" else size * size
+    sample = "icosphere100k" if kind == "icosphere" else "torus1m"
+    r = cpu_reference_steps_per_s(sample, full_n, max(1, min(args.steps, 3)), max(1, min(args.warmup, 1)))
+    sample_txt = ("oracle/step_port.py (torch-CPU port of the reference step) on %s = %d vertices, %.0f ms/step, "
+                  "scaled x%.2f to %d vertices" % (sample, r["sample_vertices"], r["sample_ms"],
+                                                  full_n / r["sample_vertices"], full_n))
+    line = {"impl": "reference", "metric": "train_steps_per_s", "value": r["steps_per_s"], "unit": "steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "vertices": full_n, "k": k, "hidden": HIDDEN},
+            "cpu_baseline": {"value": r["steps_per_s"], "unit": "steps/s", "cores": r["threads"], "kind": "port",
+                             "sample": sample_txt},
+            "e2e": {"value": r["steps_per_s"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    pkg().require_library()
+    cabi = pkg("_cabi")
+    if SRC not in sys.path:
+        sys.path.insert(0, SRC)
+    import config as cfg_mod
+    import multigrid_model
+
+    w = build_host_workload(args.workload)
+    n, k = w["verts"].shape[0], w["k"]
+    cfg = cfg_mod.PINNConfig.from_yaml(os.path.join(SRC, "parameters.yml"))
+    cfg.n_modes, cfg.mlp_mode, cfg.seed, cfg.hidden_layers = k, args.mlp_mode, 0, HIDDEN
+    devnull = open(os.devnull, "w")
+    stdout, sys.stdout = sys.stdout, devnull                 # the drop-in modules print like the reference
+    try:
+        gnn = multigrid_model.MultigridGNN(cfg)
+        edges = torch.from_numpy(w["edges"])
+        U_norm = gnn._normalize_eigenvectors([w["U0"]], [w["M"]])
+        vals_rr, _ = gnn.refine_eigenvectors(w["modes"].astype(np.float32), w["K"], w["M"])
+        lam0 = torch.from_numpy(vals_rr.astype(np.float32))
+        x_feats, edge_all, A_norm = gnn._build_features([w["verts"]], U_norm, [lam0], [edges], [w["K"]], [w["M"]])
+        gnn._initialize_model(x_feats.shape[1], k, HIDDEN, 0.0)
+        opt, sched = gnn._create_optimizer(gnn.lr, gnn.weight_decay)
+        if world > 1:
+            dist_engine = pkg("dist_engine")
+            eng = dist_engine.make_sharded_engine(gnn, x_feats, edge_all, U_norm[0], w["K"], w["M"], lam0, opt, rank, world)
+        else:
+            eng = gnn._make_engine(x_feats, edge_all, A_norm, U_norm[0], [w["K"]], [w["M"]], lam0, [0], opt)
+    finally:
+        sys.stdout = stdout
+    lam_err = None
+    if w["lam_analytic"] is not None:
+        ref = w["lam_analytic"]
+        nz = ref > 0
+        lam_err = float(np.max(np.abs(np.sort(vals_rr)[nz] - ref[nz]) / ref[nz]))
+    d_in = eng.h.shape[1]
+    flops_v = mlp_flops_per_vertex(d_in, HIDDEN, k)
+    nnz = w["K"].nnz
+    epoch0 = 2500                                            # mid-ramp: correction scale 5.0, non-zero gradients
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    for i in range(args.warmup):
+        eng.step(epoch0 + i)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = cabi.launch_counter
+    marks_all = []
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record()
+    for i in range(args.steps):
+        marks = []
+        eng.step(epoch0 + args.warmup + i, marks=marks)
+        marks_all.append(marks)
+    t_end.record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    launches = cabi.launch_counter - launches0
+    ms_total = t_start.elapsed_time(t_end)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    phase = {}
+    for marks in marks_all:
+        for (a, ea), (b, eb) in zip(marks[:-1], marks[1:]):
+            phase[b] = phase.get(b, 0.0) + ea.elapsed_time(eb)
+    phase = {p: v / args.steps for p, v in phase.items()}
+    loss_now = float(eng.loss_acc.cpu().numpy()[5])
+
+    # ---- SpMM alone (HBM roofline of the sparse operator)
+    pair = eng.pairs[-1]
+    s = eng._level_slices(len(eng.pairs) - 1)
+    ops = pkg("ops")
+    reps = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ops.spmm2(pair, eng.U_pred[s], out_K=eng.KU[s], out_M=eng.MU[s])
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        ops.spmm2(pair, eng.U_pred[s], out_K=eng.KU[s], out_M=eng.MU[s])
+    e1.record()
+    torch.cuda.synchronize()
+    spmm_ms = e0.elapsed_time(e1) / reps
+    n_loc = pair.n
+    spmm_bytes = 12 * pair.K.nnz + 4 * (n_loc + 1) + 12 * n_loc * k
+    peaks = measured_peaks()
+
+    # ---- end to end: inputs in pinned host memory every step, loss read back every step
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        h_host = eng.h.cpu().pin_memory()
+        ub_host = eng.U_base.cpu().pin_memory()
+        for i in range(2):
+            eng.step_from_host(h_host, ub_host, epoch0 + i)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            eng.step_from_host(h_host, ub_host, epoch0 + i)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.steps
+        e2e = {"value": 1.0 / dt, "unit": "steps/s", "h2d_bytes_per_step": int(h_host.numel() * 4 + ub_host.numel() * 4),
+               "d2h_bytes_per_step": 48}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    mlp_ms = phase.get("mlp_fwd", 0.0) + phase.get("mlp_bwd", 0.0)
+    n_global = n
+    tflops = flops_v * n_global / world / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
+    tensor_peak = peaks["bf16_sustained"]
+    roofline = {"bound": "tensor", "kernel": "corrector MLP forward+backward (%s)" % args.mlp_mode, "achieved": tflops,
+                "peak": tensor_peak, "unit": "TFLOP/s", "frac": tflops / tensor_peak, "traffic": None,
+                "peak_source": peaks["source"] + " bf16 sustained", "ms_per_step": mlp_ms,
+                "flop_per_vertex": flops_v}
+    spmm_gbs = spmm_bytes / (spmm_ms * 1e-3) / 1e9
+    spmm_roof = {"bound": "hbm", "kernel": "ep_spmm2_csr_f32 (K U and M U, shared pattern)", "achieved": spmm_gbs,
+                 "peak": peaks["hbm"], "unit": "GB/s", "frac": spmm_gbs / peaks["hbm"], "ms": spmm_ms,
+                 "bytes_per_launch": spmm_bytes, "traffic": None}
+    cpu = None
+    if not args.no_cpu_baseline:
+        kind, size, _ = WORKLOADS[args.workload]
+        sample = "icosphere100k" if kind == "icosphere" else "torus1m"
+        if n_global < 150000:
+            sample = args.workload
+        r = cpu_reference_steps_per_s(sample, n_global, 2, 1)
+        cpu = {"value": r["steps_per_s"], "unit": "steps/s", "cores": r["threads"], "kind": "port",
+               "sample": "oracle/step_port.py on %s (%d vertices, %.0f ms/step) scaled to %d vertices"
+                         % (sample, r["sample_vertices"], r["sample_ms"], n_global)}
+    line = {"metric": "train_steps_per_s", "value": 1000.0 / ms_step, "unit": "steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32" if args.mlp_mode == "fp32" else "bf16",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "vertices": n_global, "k": k, "hidden": HIDDEN, "mlp_in": d_in,
+                       "nnz_per_operator": int(nnz), "mlp_mode": args.mlp_mode, "levels": 1,
+                       "parallelism": "vertex-shard x%d" % world,
+                       "l2": "inputs larger than L2 (U, KU, MU, activations >> 126 MB)"},
+            "clocks": clk, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,
+            "spmm_roofline": spmm_roof, "cpu_baseline": cpu,
+            "phase_ms": phase, "loss": loss_now, "lambda_rel_err_rayleigh_ritz": lam_err}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="icosphere1m", choices=sorted(WORKLOADS))
+    ap.add_argument("--mlp-mode", default=os.environ.get("EP_MLP_MODE", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,214 @@
+"""Explicit (autograd-free) training step of the corrector network on the eigen-loss.
+
+One `step()` is one epoch body of the reference loop (src/multigrid_model.py:237-261):
+    corrector forward -> U_pred = U_base + scale * corr -> per level K U, M U -> Rayleigh
+    quotient / residual / Gram terms -> analytic backward -> MLP backward -> clip + Adam.
+All buffers are allocated once; every arithmetic kernel is one of ours (include/eigenpinns_b200.h).
+
+Two MLP back ends share this driver:
+  "fp32"  layer-by-layer SIMT GEMMs, fp32 end to end       (parity mode, <= 1e-5 vs. the reference)
+  "bf16"  fused tcgen05 forward / backward over vertex tiles (perf mode, tolerance stated in DESIGN.md)
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import ops
+from ._cabi import call, query, EpError
+
+
+class FlatParams:
+    """Weights and biases of the corrector MLP in ONE contiguous fp32 buffer (plus gradient and
+    Adam moments of the same shape).  nn.Module parameters are re-pointed at views of it so the
+    module's state_dict keeps working while the optimiser kernel updates everything in one launch."""
+
+    def __init__(self, weights, biases, device):
+        self.shapes = [(tuple(w.shape), tuple(b.shape)) for w, b in zip(weights, biases)]
+        total = sum(w.numel() + b.numel() for w, b in zip(weights, biases))
+        self.flat = torch.empty(total, dtype=torch.float32, device=device)
+        self.grad = torch.zeros_like(self.flat)
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.W, self.b, self.dW, self.db = [], [], [], []
+        off = 0
+        for w, b in zip(weights, biases):
+            for src, store, gstore in ((w, self.W, self.dW), (b, self.b, self.db)):
+                n = src.numel()
+                view = self.flat[off:off + n].view(src.shape)
+                view.copy_(src.detach().to(device=device, dtype=torch.float32))
+                store.append(view)
+                gstore.append(self.grad[off:off + n].view(src.shape))
+                off += n
+        self.step_count = 0
+        self.sq_norm = torch.zeros(1, dtype=torch.float64, device=device)
+
+    @classmethod
+    def adopt(cls, linears):
+        """Build from nn.Linear modules and make their parameters views of the flat buffer."""
+        dev = linears[0].weight.device
+        fp = cls([l.weight for l in linears], [l.bias for l in linears], dev)
+        for lin, W, b in zip(linears, fp.W, fp.b):
+            lin.weight.data = W
+            lin.bias.data = b
+        return fp
+
+    @property
+    def dims(self):
+        return [self.W[0].shape[1]] + [w.shape[0] for w in self.W]
+
+
+class Fp32Mlp:
+    """Layer-wise fp32 forward / backward with saved activations."""
+
+    def __init__(self, n, params: FlatParams, device):
+        self.p = params
+        dims = params.dims
+        self.acts = [torch.empty((n, d), dtype=torch.float32, device=device) for d in dims[1:]]
+        wmax = max(dims[1:-1]) if len(dims) > 2 else dims[0]
+        self.dx = [torch.empty((n, wmax), dtype=torch.float32, device=device) for _ in range(2)]
+
+    def forward(self, h):
+        x = h
+        L = len(self.p.W)
+        for l in range(L):
+            ops.linear_fwd(x, self.p.W[l], self.p.b[l], relu=(l < L - 1), out=self.acts[l])
+            x = self.acts[l]
+        return x                                    # corr_raw (n x k)
+
+    def backward(self, h, d_out):
+        L = len(self.p.W)
+        dy = d_out
+        for l in range(L - 1, -1, -1):
+            x = self.acts[l - 1] if l > 0 else h
+            need_dx = l > 0
+            dx = self.dx[l & 1][:, :x.shape[1]] if need_dx else None
+            ops.linear_bwd(x, self.p.W[l], dy, need_dx, relu_mask=need_dx, dW=self.p.dW[l], db=self.p.db[l], dX=dx)
+            dy = dx
+
+
+class StepConfig:
+    def __init__(self, lr=1e-3, weight_decay=1e-5, corr_scale=10.0, w_res=1000.0, w_orth=10.0, w_trace=0.0,
+                 w_order=0.0, w_eigen=0.0, grad_clip=10.0, beta1=0.9, beta2=0.999, eps=1e-8, ramp_epochs=5000.0):
+        self.lr, self.weight_decay, self.corr_scale = lr, weight_decay, corr_scale
+        self.w_res, self.w_orth, self.w_trace, self.w_order, self.w_eigen = w_res, w_orth, w_trace, w_order, w_eigen
+        self.grad_clip, self.beta1, self.beta2, self.eps = grad_clip, beta1, beta2, eps
+        self.ramp_epochs = ramp_epochs
+
+
+class TrainStepEngine:
+    """Single-GPU step.  h: (sum N) x 2d corrector input, U_base: (sum N) x k, pairs: OperatorPair per
+    level, offsets: first row of each level in the stacked arrays."""
+
+    def __init__(self, h, U_base, pairs, offsets, params: FlatParams, cfg: StepConfig, lam_target=None,
+                 mlp_mode="fp32"):
+        self.h, self.U_base, self.pairs, self.cfg, self.params = h, U_base.contiguous(), pairs, cfg, params
+        self.offsets = [int(o) for o in offsets]
+        self.dev = h.device
+        self.n_total, self.k = U_base.shape
+        k = self.k
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.U_pred = torch.empty((self.n_total, k), **f32)
+        self.KU = torch.empty((self.n_total, k), **f32)
+        self.MU = torch.empty((self.n_total, k), **f32)
+        self.KU_bar = torch.empty((self.n_total, k), **f32)
+        self.MU_bar = torch.empty((self.n_total, k), **f32)
+        self.D = torch.empty((self.n_total, k), **f32)
+        self.dCorr = torch.empty((self.n_total, k), **f32)
+        ws = ops.EigenWorkspace.get(k, self.dev)
+        self.partials = [torch.empty(ws.plen, dtype=torch.float64, device=self.dev) for _ in pairs]
+        self.coefs = [torch.empty(ws.clen, **f32) for _ in pairs]
+        self.lams = [torch.empty(k, **f32) for _ in pairs]
+        self.loss_acc = torch.zeros(6, dtype=torch.float64, device=self.dev)
+        self.lam_target = lam_target.to(**f32).contiguous() if lam_target is not None else None
+        self.mlp_mode = mlp_mode
+        if mlp_mode == "fp32":
+            self.mlp = Fp32Mlp(self.n_total, params, self.dev)
+        elif mlp_mode == "bf16":
+            from .mlp_tc import TcMlp
+            self.mlp = TcMlp(self.n_total, params, self.dev, h)
+        else:
+            raise ValueError("mlp_mode must be 'fp32' or 'bf16'")
+        self.launches_per_step = None
+
+    # ---- pieces (also used one by one by the tests)
+    def scale_for(self, epoch):
+        return self.cfg.corr_scale * min(1.0, epoch / self.cfg.ramp_epochs)
+
+    def forward(self, scale):
+        corr = self.mlp.forward(self.h)
+        ops.axpy_out(self.U_base, corr, scale, out=self.U_pred)
+        return corr
+
+    def _level_slices(self, li):
+        off, n = self.offsets[li], self.pairs[li].n
+        return slice(off, off + n)
+
+    def loss_forward(self):
+        c = self.cfg
+        self.loss_acc.zero_()
+        for li, pair in enumerate(self.pairs):
+            s = self._level_slices(li)
+            ops.spmm2(pair, self.U_pred[s], out_K=self.KU[s], out_M=self.MU[s])
+            ops.eigen_partials(self.U_pred[s], self.KU[s], self.MU[s], out=self.partials[li])
+            self._reduce_partials(li)
+            ops.eigen_finalize(self.k, self._n_global(li), self.partials[li], c.w_res, c.w_orth, self.loss_acc,
+                               coef=self.coefs[li], lam_out=self.lams[li], level0=(li == 0),
+                               lam_target=self.lam_target, w_trace=c.w_trace, w_order=c.w_order, w_eigen=c.w_eigen)
+
+    def loss_backward(self, scale):
+        for li, pair in enumerate(self.pairs):
+            s = self._level_slices(li)
+            ops.eigen_bwd_prepare(self.U_pred[s], self.KU[s], self.MU[s], self.coefs[li], self.KU_bar[s],
+                                  self.MU_bar[s], self.D[s])
+            ops.spmm2_sum(pair.KT, pair.MT, self.KU_bar[s], self.MU_bar[s], self.D[s], scale, out=self.dCorr[s])
+
+    def optimizer_step(self, lr):
+        p, c = self.params, self.cfg
+        self._reduce_grads()
+        ops.grad_sqnorm(p.grad, p.sq_norm)
+        p.step_count += 1
+        ops.adam_clip_step(p.flat, p.grad, p.m, p.v, lr, c.beta1, c.beta2, c.eps, c.weight_decay, p.step_count,
+                           c.grad_clip, p.sq_norm)
+
+    # hooks for the vertex-sharded engine
+    def _n_global(self, li):
+        return self.pairs[li].n
+
+    def _reduce_partials(self, li):
+        pass
+
+    def _reduce_grads(self):
+        pass
+
+    def step(self, epoch, lr=None, marks=None):
+        """One epoch body.  Returns the device tensor loss_acc = [res, orth, trace, order, eigen, total]
+        (weighted, fp64); reading it on the host is the caller's one sync per step.
+        marks: optional list that receives (phase, cuda event) pairs recorded on the current stream."""
+        def mark(name):
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((name, ev))
+        scale = self.scale_for(epoch)
+        mark("start")
+        self.forward(scale)
+        mark("mlp_fwd")
+        self.loss_forward()
+        mark("loss_fwd")
+        self.loss_backward(scale)
+        mark("loss_bwd")
+        self.mlp.backward(self.h, self.dCorr)
+        mark("mlp_bwd")
+        self.optimizer_step(self.cfg.lr if lr is None else lr)
+        mark("optim")
+        return self.loss_acc
+
+    def step_from_host(self, h_host, U_base_host, epoch, lr=None):
+        """End-to-end variant: this step's inputs arrive in (pinned) host memory, the loss goes back to the
+        host.  Returns the six loss terms as a numpy array (one synchronising D2H copy)."""
+        self.h.copy_(h_host, non_blocking=True)
+        self.U_base.copy_(U_base_host, non_blocking=True)
+        if hasattr(self.mlp, "input_changed"):
+            self.mlp.input_changed(self.h)
+        return self.step(epoch, lr).cpu().numpy()

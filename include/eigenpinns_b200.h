@@ -1,0 +1,232 @@
+/* eigenpinns_b200.h — C ABI of the B200 (sm_100a) kernels behind the eigen-pinns hot path.
+ *
+ * The reference (bornexmachina/eigen-pinns) is pure Python and has no FFI of its own; the
+ * boundary it exposes is the Python method surface of MultigridGNN / SimpleCorrector /
+ * SpectralCorrector and the two sampler functions.  Every entry point below names the
+ * reference lines whose arithmetic it replaces (paths under /root/reference/src).  The
+ * Python host layer (eigen-pinns_b200/) binds these with ctypes; INTEGRATION.md shows the
+ * stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary
+ *   - all array pointers are DEVICE pointers unless the function name ends in _host; the tiny
+ *     parameter arrays `dims`, `lo` (voxel grid) and `bias` / `W` / `dW` / `db` pointer tables are
+ *     HOST arrays (of device pointers where they are tables)
+ *   - dense matrices are row-major with an explicit leading dimension (elements)
+ *   - CSR: int32 rowptr[n+1], int32 col[nnz], fp32 val[nnz]
+ *   - every call takes the CUDA stream it is enqueued on (cudaStream_t as void*); nothing
+ *     synchronises unless stated; no hidden allocation: workspaces are sized by *_workspace_bytes
+ *   - return value: 0 = EP_OK, negative = error (see ep_status); ep_last_error_string()
+ *     describes the last failure on the calling thread; nothing throws
+ */
+#ifndef EIGENPINNS_B200_H
+#define EIGENPINNS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define EP_API __attribute__((visibility("default")))
+#else
+#define EP_API
+#endif
+
+typedef void* ep_stream_t;
+
+enum ep_status {
+  EP_OK = 0,
+  EP_ERR_INVALID = -1,      /* bad argument (null pointer, negative size, misalignment) */
+  EP_ERR_CUDA = -2,         /* a CUDA runtime call failed */
+  EP_ERR_UNSUPPORTED = -3,  /* shape outside what the kernels are instantiated for */
+  EP_ERR_WORKSPACE = -4     /* workspace too small */
+};
+
+/* ---- library ------------------------------------------------------------------------- */
+EP_API int ep_version(void);                               /* 10000*major + 100*minor + patch */
+EP_API const char* ep_last_error_string(void);
+/* sm_count, compute capability of the current device; fails (EP_ERR_CUDA) without a GPU. */
+EP_API int ep_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- sparse operators: torch.sparse.mm(K_t, U), torch.sparse.mm(M_t, U) ----------------
+ * replaces multigrid_model.py:309-310 (loss), :126,:375 (normalisation), :403-404 (Rayleigh-
+ * Ritz), :183-184 (features) and the autograd transposes behind :258.  The per-epoch
+ * scipy->torch COO conversion of utils.py:14-20 (called at multigrid_model.py:306-307)
+ * disappears: operators are converted to CSR fp32/int32 once and stay resident in HBM. */
+/* Y = A X.  X: n_cols_of_A x k (ldx), Y: n_rows x k (ldy). */
+EP_API int ep_spmm_csr_f32(int n_rows, int k, const int32_t* rowptr, const int32_t* col, const float* val,
+                    const float* X, int ldx, float* Y, int ldy, ep_stream_t stream);
+/* YA = A X and YB = B X for two operators that share one sparsity pattern (FEM K and M):
+ * each gathered row of X is read once for both products. */
+EP_API int ep_spmm2_csr_f32(int n_rows, int k, const int32_t* rowptr, const int32_t* col,
+                     const float* valA, const float* valB, const float* X, int ldx,
+                     float* YA, float* YB, int ldy, ep_stream_t stream);
+/* Y = out_scale * (A XA + B XB + D)   (D may be NULL).  Backward of the eigen-loss:
+ * U_bar = K^T KU_bar + M^T MU_bar + D; pass the CSR of the transposes
+ * (identical to K, M for the symmetric FEM / tufted operators). */
+EP_API int ep_spmm2_sum_csr_f32(int n_rows, int k, const int32_t* rowptr, const int32_t* col,
+                         const float* valA, const float* valB, const float* XA, const float* XB,
+                         int ldx, const float* D, int ldd, float out_scale, float* Y, int ldy,
+                         ep_stream_t stream);
+
+/* ---- corrector input: h = cat([x, agg], dim=1) -----------------------------------------
+ * SimpleCorrector.forward, corrector_model.py:23-30: agg_i = (sum over edges (i<-j) of x_j) /
+ * max(deg_i, 1), edges given as CSR over destination rows (rowptr/col), summed in edge order.
+ * H: n x 2d (ldh >= 2d): H[:, :d] = x, H[:, d:] = agg. */
+EP_API int ep_neighbor_mean_concat_f32(int n, int d, const int32_t* rowptr, const int32_t* col,
+                                const float* x, int ldx, float* H, int ldh, ep_stream_t stream);
+/* SpectralCorrector.forward, corrector_model.py:76-79: H = [x | A_norm x], A_norm as CSR. */
+EP_API int ep_spmm_concat_f32(int n, int d, const int32_t* rowptr, const int32_t* col, const float* val,
+                       const float* x, int ldx, float* H, int ldh, ep_stream_t stream);
+
+/* ---- eigen-loss: multigrid_model.py:291-348 --------------------------------------------
+ * Phase 1 (per level, per rank): column/Gram partial sums in fp64,
+ *   out[0 .. k*k)        G[a*k+b]  = sum_i U[i,a] * MU[i,b]          (:321; diag = den of :313)
+ *   out[k*k + 0k ..)     num[j]    = sum_i U[i,j] * KU[i,j]           (:313)
+ *   out[k*k + 1k ..)     sKK[j]    = sum_i KU[i,j]^2
+ *   out[k*k + 2k ..)     sKM[j]    = sum_i KU[i,j] * MU[i,j]
+ *   out[k*k + 3k ..)     sMM[j]    = sum_i MU[i,j]^2
+ * (the last three give sum_i (KU - lam MU)^2 of :317-318 without a second pass; they are
+ * accumulated in fp64 so the expansion does not cancel).  Partials of all ranks are summed
+ * (allreduce) before phase 2.  Deterministic: fixed grid, fixed reduction order. */
+EP_API size_t ep_eigen_partials_len(int k);                        /* k*k + 4*k doubles */
+EP_API size_t ep_eigen_partials_workspace_bytes(int k);
+EP_API int ep_eigen_partials_f32(int n, int k, const float* U, int ldu, const float* KU, const float* MU,
+                          int ld, double* out, void* workspace, size_t workspace_bytes,
+                          ep_stream_t stream);
+
+/* Phase 2 (per level, one tiny launch): from the summed partials compute
+ *   lam_j = num_j / (G_jj + 1e-12);  L_res = sum_j(sKK - 2 lam sKM + lam^2 sMM) / (n_global k);
+ *   L_orth = sum_ab (G_ab - I_ab)^2 / k;  and for level 0 the eigenvalue terms of :326-348
+ *   (trace = mean lam, order = sum relu(lam_j - lam_{j+1}), eigen = mean (lam - lam_target)^2).
+ * loss_acc[0..5] += {w_res L_res, w_orth L_orth, w_trace trace, w_order order, w_eigen eigen, total}
+ * coef receives what the backward needs (layout below, fp32):
+ *   coef[0] = c_res = 2 w_res / (n_global k)
+ *   coef[1 .. 1+k)      lam
+ *   coef[1+k .. 1+2k)   num_bar   (dL/dnum)
+ *   coef[1+2k .. 1+3k)  den_bar   (dL/dden)
+ *   coef[1+3k .. )      G_bar[a*k+b] = 2 w_orth / k * (G_ab - I_ab)
+ * lam_target may be NULL (eigen term = 0).  level0 != 0 enables the :326-348 terms.
+ * lam_bar_extra (k floats, may be NULL) is added to dL/dlam: the gradient arriving from any
+ * further use of the returned eigenvalues (autograd path of the drop-in modules). */
+EP_API size_t ep_eigen_coef_len(int k);                            /* 1 + 3k + k*k floats */
+EP_API int ep_eigen_finalize_f32(int k, double n_global, const double* partials, float w_res, float w_orth,
+                          int level0, const float* lam_target, float w_trace, float w_order,
+                          float w_eigen, const float* lam_bar_extra, float* lam_out, float* coef,
+                          double* loss_acc, ep_stream_t stream);
+
+/* Phase 3 (backward, per level): analytic gradient of the loss w.r.t. the three tensors it
+ * was built from (what autograd derives from :309-322):
+ *   R_bar  = c_res (KU - MU lam)
+ *   KU_bar = R_bar + U num_bar
+ *   MU_bar = -R_bar lam + U den_bar + U G_bar
+ *   D      = KU num_bar + MU den_bar + MU G_bar^T        (direct dependence on U)
+ * followed by ep_spmm2_sum_csr_f32(K^T, M^T, KU_bar, MU_bar, D) -> dL/dU. */
+EP_API int ep_eigen_bwd_prepare_f32(int n, int k, const float* U, int ldu, const float* KU, const float* MU,
+                             int ld, const float* coef, float* KU_bar, float* MU_bar, float* D,
+                             ep_stream_t stream);
+
+/* ---- column M-normalisation: multigrid_model.py:120-130, :366-380 ----------------------
+ * out[:, j] = U[:, j] / sqrt(colsum_j + 1e-12) where colsum_j = sum_i U_ij MU_ij is read from
+ * the diagonal of a partials block (G_jj).  */
+EP_API int ep_scale_columns_rsqrt_f32(int n, int k, const float* U, int ldu, const double* G, int ldg,
+                               double eps, float* out, int ldo, ep_stream_t stream);
+
+/* out = a + alpha * b  (U_pred = U_base + adaptive_scale * corr_raw, multigrid_model.py:243-245);
+ * alpha_dev, when non-NULL, is a device scalar that overrides alpha (graph-capturable ramp). */
+EP_API int ep_axpy_out_f32(size_t n, float alpha, const float* alpha_dev, const float* a, const float* b,
+                    float* out, ep_stream_t stream);
+
+/* ---- corrector MLP, fp32 SIMT path ("parity mode"): corrector_model.py:12-21,31 ---------
+ * Y = act(X W^T + b), W: out x in row-major (nn.Linear layout), act: 0 none, 1 ReLU. */
+EP_API int ep_linear_fwd_f32(int n, int in, int out, const float* X, int ldx, const float* W, const float* b,
+                      float* Y, int ldy, int act, ep_stream_t stream);
+/* Backward of one layer.  dY: n x out (gradient w.r.t. the pre-activation of this layer).
+ *   dX = (dY W) * [X > 0]  if dX != NULL (X is the previous layer's ReLU output, so its sign
+ *        pattern is the ReLU mask; relu_mask == 0 skips the mask for a non-ReLU input)
+ *   dW = dY^T X  (out x in),  db = column sums of dY.
+ * workspace: ep_linear_bwd_workspace_bytes(n, in, out) bytes (split-K partials, deterministic). */
+EP_API size_t ep_linear_bwd_workspace_bytes(int n, int in, int out);
+EP_API int ep_linear_bwd_f32(int n, int in, int out, const float* X, int ldx, const float* W,
+                      const float* dY, int lddy, float* dX, int lddx, int relu_mask,
+                      float* dW, float* db, void* workspace, size_t workspace_bytes,
+                      ep_stream_t stream);
+
+/* ---- corrector MLP, bf16 tcgen05 path ("perf mode") --------------------------------------
+ * Fused forward of the whole corrector network over 128-vertex tiles: TMA bulk copies stage
+ * pre-packed bf16 weights and input tiles in shared memory, tcgen05.mma accumulates in TMEM,
+ * bias + ReLU + bf16 conversion happen in the TMEM epilogue and hidden activations never
+ * leave the SM (except the bf16 copies kept for the backward pass).
+ * See csrc/mlp_tc.cu for the packed layouts; ep_mlp_tc_* return EP_ERR_UNSUPPORTED for
+ * shapes the kernel is not instantiated for (hidden width must be 256). */
+EP_API size_t ep_mlp_tc_packed_weight_bytes(int n_layers, const int* dims);
+EP_API size_t ep_mlp_tc_packed_input_bytes(int n, int in_dim);
+EP_API size_t ep_mlp_tc_act_bytes(int n, int n_layers, const int* dims);
+EP_API int ep_mlp_tc_pack_weights(int n_layers, const int* dims, const float* const* W, void* packed,
+                           void* packed_T, ep_stream_t stream);
+EP_API int ep_mlp_tc_pack_input(int n, int in_dim, const float* H, int ldh, void* packed, ep_stream_t stream);
+EP_API int ep_mlp_tc_fwd(int n, int n_layers, const int* dims, const void* packed_in, const void* packed_W,
+                  const float* const* bias, void* acts, const float* U_base, float scale,
+                  const float* scale_dev, float* corr_raw, float* U_pred, int ldu, ep_stream_t stream);
+EP_API int ep_mlp_tc_bwd(int n, int n_layers, const int* dims, const void* packed_in, const void* packed_W,
+                  const void* packed_WT, const void* acts, const float* dOut, int ldd, float dscale,
+                  const float* dscale_dev, float* const* dW, float* const* db, void* workspace,
+                  size_t workspace_bytes, ep_stream_t stream);
+EP_API size_t ep_mlp_tc_bwd_workspace_bytes(int n, int n_layers, const int* dims);
+
+/* ---- optimiser: clip_grad_norm_ + Adam(weight_decay) step, multigrid_model.py:218-220,259-260
+ * Parameters / gradients / moments live in one flat fp32 buffer each.
+ *   norm   = sqrt(sum g^2)                      (ep_grad_sqnorm_f32 -> sq_out, fp64, device)
+ *   coef   = min(1, max_norm / (norm + 1e-6));  g = coef * g + weight_decay * p
+ *   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2
+ *   p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+ * lr_dev (device scalar, may be NULL) overrides lr so a captured graph can follow the
+ * ReduceLROnPlateau schedule of :221-223. */
+EP_API int ep_grad_sqnorm_f32(size_t n, const float* g, double* sq_out, ep_stream_t stream);
+EP_API int ep_adam_clip_step_f32(size_t n, float* p, const float* g, float* m, float* v, float lr,
+                          const float* lr_dev, float beta1, float beta2, float eps,
+                          float weight_decay, int step, float max_norm, const double* sq_norm,
+                          ep_stream_t stream);
+
+/* ---- samplers: samplers.py:97-143 (farthest point), :9-94 (voxel) ----------------------
+ * fp64, bit-exact w.r.t. numpy: d = sqrt((dx*dx + dy*dy) + dz*dz) with IEEE round-to-nearest
+ * and no FMA contraction, running minimum, first index wins arg-max / arg-min ties.
+ * pts: N x 3 row-major doubles.  out_order: n_samples int64 (selection order; out_order[0]
+ * = start).  One persistent cooperative kernel runs all n_samples-1 dependent iterations. */
+EP_API size_t ep_fps_workspace_bytes(int64_t n_points);
+EP_API int ep_fps_f64(int64_t n_points, const double* pts, int n_samples, int64_t start,
+               int64_t* out_order, void* workspace, size_t workspace_bytes, ep_stream_t stream);
+/* Host-buffer variant (allocates, copies in, runs, copies out, synchronises). */
+EP_API int ep_fps_f64_host(int64_t n_points, const double* pts_host, int n_samples, int64_t start,
+                    int64_t* out_order_host);
+
+/* Axis-aligned bounds: lo_hi[0..3) = min, lo_hi[3..6) = max  (samplers.py:21-22). */
+EP_API int ep_bounds_f64(int64_t n_points, const double* pts, double* lo_hi, ep_stream_t stream);
+/* One voxel pass for one voxel size (body of the scale loop, samplers.py:45-74): cell =
+ * clip(trunc((p - lo) / voxel), 0, dims-1); id = cx*dy*dz + cy*dz + cz; for every occupied
+ * voxel pick the point nearest the voxel centre lo + (c + 0.5) * voxel (first index on ties).
+ * out_idx receives the picks in ascending voxel id, *out_count (device int64) their number.
+ * max_out bounds the write (count is still the true total). */
+EP_API size_t ep_voxel_workspace_bytes(int64_t n_points, int64_t n_voxels);
+EP_API int ep_voxel_select_f64(int64_t n_points, const double* pts, const double* lo, double voxel,
+                        const int64_t* dims, int64_t* out_idx, int64_t max_out, int64_t* out_count,
+                        void* workspace, size_t workspace_bytes, ep_stream_t stream);
+EP_API int ep_voxel_select_f64_host(int64_t n_points, const double* pts_host, const double* lo, double voxel,
+                             const int64_t* dims, int64_t* out_idx_host, int64_t max_out,
+                             int64_t* out_count_host);
+
+/* ---- multi-GPU plumbing: halo rows --------------------------------------------------------
+ * dst[r, :] = src[idx[r], :]  (pack the boundary rows of U that a peer needs). */
+EP_API int ep_gather_rows_f32(int n_idx, int k, const int32_t* idx, const float* src, int lds,
+                       float* dst, int ldd, ep_stream_t stream);
+/* dst[idx[r], :] += src[r, :]   (idx values must be unique within one call). */
+EP_API int ep_scatter_add_rows_f32(int n_idx, int k, const int32_t* idx, const float* src, int lds,
+                            float* dst, int ldd, ep_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EIGENPINNS_B200_H */

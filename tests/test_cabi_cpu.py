@@ -1,0 +1,77 @@
+"""CPU-side checks of the boundary: the shared library loads and exports every symbol the public
+header declares, the ctypes table mirrors the header, and the product refuses CPU tensors."""
+import ctypes
+import importlib
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "eigenpinns_b200.h")
+
+
+def _declared():
+    text = open(HEADER).read()
+    return sorted(set(re.findall(r"EP_API\s+[\w\s\*]+?\b(ep_\w+)\s*\(", text)))
+
+
+def test_header_declares_entry_points():
+    names = _declared()
+    assert len(names) >= 35
+    for must in ("ep_spmm2_csr_f32", "ep_eigen_partials_f32", "ep_fps_f64", "ep_voxel_select_f64",
+                 "ep_linear_fwd_f32", "ep_adam_clip_step_f32", "ep_mlp_tc_fwd"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    cabi = importlib.import_module("eigen-pinns_b200._cabi")
+    lib = cabi.load()
+    for name in _declared():
+        assert hasattr(lib, name), "library does not export " + name
+    assert lib.ep_version() >= 100
+
+
+def test_ctypes_table_matches_header():
+    cabi = importlib.import_module("eigen-pinns_b200._cabi")
+    assert sorted(cabi.SIGNATURES) == _declared()
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    for name, (_, args) in cabi.SIGNATURES.items():
+        m = re.search(r"\b%s\s*\(([^;]*?)\)\s*;" % name, text, flags=re.S)
+        assert m, name
+        params = m.group(1).strip()
+        n = 0 if params in ("void", "") else params.count(",") + 1
+        assert n == len(args), "%s: header has %d parameters, ctypes table %d" % (name, n, len(args))
+
+
+def test_sizes_without_gpu():
+    cabi = importlib.import_module("eigen-pinns_b200._cabi")
+    assert cabi.query("ep_eigen_partials_len", 32) == 32 * 32 + 4 * 32
+    assert cabi.query("ep_eigen_coef_len", 64) == 1 + 3 * 64 + 64 * 64
+
+
+def test_ops_reject_cpu_tensors():
+    import torch
+    ops = importlib.import_module("eigen-pinns_b200.ops")
+    cabi = importlib.import_module("eigen-pinns_b200._cabi")
+    with pytest.raises((cabi.EpError, AssertionError, RuntimeError)):
+        ops.linear_fwd(torch.zeros(4, 4), torch.zeros(4, 4), torch.zeros(4), relu=False)
+
+
+def test_trainer_refuses_to_run_without_gpu():
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    src = os.path.join(ROOT, "eigen-pinns_b200", "src")
+    sys.path.insert(0, src)
+    try:
+        for m in ("config", "multigrid_model", "corrector_model", "utils", "Mesh", "mesh_helpers", "samplers"):
+            sys.modules.pop(m, None)
+        import config
+        import multigrid_model
+        cfg = config.PINNConfig.from_yaml(os.path.join(src, "parameters.yml"))
+        with pytest.raises(RuntimeError):
+            multigrid_model.MultigridGNN(cfg)
+    finally:
+        sys.path.remove(src)
