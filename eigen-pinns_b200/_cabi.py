@@ -36,15 +36,17 @@ SIGNATURES = {
     "ep_linear_bwd_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
     "ep_linear_bwd_f32": (c_int, [c_int, c_int, c_int, c_p, c_int, c_p, c_p, c_int, c_p, c_int, c_int,
                                   c_p, c_p, c_p, c_sz, c_p]),
-    "ep_mlp_tc_packed_weight_bytes": (c_sz, [c_int, c_p]),
-    "ep_mlp_tc_packed_input_bytes": (c_sz, [c_int, c_int]),
-    "ep_mlp_tc_act_bytes": (c_sz, [c_int, c_int, c_p]),
-    "ep_mlp_tc_pack_weights": (c_int, [c_int, c_p, c_p, c_p, c_p, c_p]),
-    "ep_mlp_tc_pack_input": (c_int, [c_int, c_int, c_p, c_int, c_p, c_p]),
-    "ep_mlp_tc_fwd": (c_int, [c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_int, c_p]),
-    "ep_mlp_tc_bwd": (c_int, [c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_f, c_p, c_p, c_p,
-                              c_p, c_sz, c_p]),
-    "ep_mlp_tc_bwd_workspace_bytes": (c_sz, [c_int, c_int, c_p]),
+    "ep_tc_pad_features": (c_int, [c_int, c_int]),
+    "ep_tc_packed_rows_bytes": (c_sz, [c_int, c_int]),
+    "ep_tc_packed_weight_bytes": (c_sz, [c_int, c_int]),
+    "ep_tc_pack_rows_bf16": (c_int, [c_int, c_int, c_int, c_p, c_int, c_p, c_p]),
+    "ep_tc_pack_weight_bf16": (c_int, [c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p]),
+    "ep_tc_linear_fwd_bf16": (c_int, [c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_int, c_p, c_p]),
+    "ep_tc_linear_final_bf16": (c_int, [c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_int, c_p, c_f, c_p,
+                                        c_p, c_int, c_p]),
+    "ep_tc_linear_dx_bf16": (c_int, [c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_p]),
+    "ep_tc_dw_workspace_bytes": (c_sz, []),
+    "ep_tc_linear_dw_bf16": (c_int, [c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "ep_grad_sqnorm_f32": (c_int, [c_sz, c_p, c_p, c_p]),
     "ep_adam_clip_step_f32": (c_int, [c_sz, c_p, c_p, c_p, c_p, c_f, c_p, c_f, c_f, c_f, c_f, c_int, c_f,
                                       c_p, c_p]),
@@ -73,7 +75,8 @@ KERNELS_PER_CALL = {
     "ep_scale_columns_rsqrt_f32": 1, "ep_axpy_out_f32": 1, "ep_linear_fwd_f32": 1, "ep_linear_bwd_f32": 5,
     "ep_grad_sqnorm_f32": 2, "ep_adam_clip_step_f32": 1, "ep_fps_f64": 1, "ep_bounds_f64": 2,
     "ep_voxel_select_f64": 6, "ep_gather_rows_f32": 1, "ep_scatter_add_rows_f32": 1,
-    "ep_mlp_tc_pack_weights": 1, "ep_mlp_tc_pack_input": 1, "ep_mlp_tc_fwd": 1, "ep_mlp_tc_bwd": 1,
+    "ep_tc_pack_rows_bf16": 1, "ep_tc_pack_weight_bf16": 1, "ep_tc_linear_fwd_bf16": 1, "ep_tc_linear_final_bf16": 1,
+    "ep_tc_linear_dx_bf16": 1, "ep_tc_linear_dw_bf16": 2,
 }
 launch_counter = 0
 

@@ -156,26 +156,38 @@ EP_API int ep_linear_bwd_f32(int n, int in, int out, const float* X, int ldx, co
                       ep_stream_t stream);
 
 /* ---- corrector MLP, bf16 tcgen05 path ("perf mode") --------------------------------------
- * Fused forward of the whole corrector network over 128-vertex tiles: TMA bulk copies stage
- * pre-packed bf16 weights and input tiles in shared memory, tcgen05.mma accumulates in TMEM,
- * bias + ReLU + bf16 conversion happen in the TMEM epilogue and hidden activations never
- * leave the SM (except the bf16 copies kept for the backward pass).
- * See csrc/mlp_tc.cu for the packed layouts; ep_mlp_tc_* return EP_ERR_UNSUPPORTED for
- * shapes the kernel is not instantiated for (hidden width must be 256). */
-EP_API size_t ep_mlp_tc_packed_weight_bytes(int n_layers, const int* dims);
-EP_API size_t ep_mlp_tc_packed_input_bytes(int n, int in_dim);
-EP_API size_t ep_mlp_tc_act_bytes(int n, int n_layers, const int* dims);
-EP_API int ep_mlp_tc_pack_weights(int n_layers, const int* dims, const float* const* W, void* packed,
-                           void* packed_T, ep_stream_t stream);
-EP_API int ep_mlp_tc_pack_input(int n, int in_dim, const float* H, int ldh, void* packed, ep_stream_t stream);
-EP_API int ep_mlp_tc_fwd(int n, int n_layers, const int* dims, const void* packed_in, const void* packed_W,
-                  const float* const* bias, void* acts, const float* U_base, float scale,
-                  const float* scale_dev, float* corr_raw, float* U_pred, int ldu, ep_stream_t stream);
-EP_API int ep_mlp_tc_bwd(int n, int n_layers, const int* dims, const void* packed_in, const void* packed_W,
-                  const void* packed_WT, const void* acts, const float* dOut, int ldd, float dscale,
-                  const float* dscale_dev, float* const* dW, float* const* db, void* workspace,
-                  size_t workspace_bytes, ep_stream_t stream);
-EP_API size_t ep_mlp_tc_bwd_workspace_bytes(int n, int n_layers, const int* dims);
+ * Same Linear / ReLU network, evaluated layer by layer on the 5th-generation tensor cores:
+ * bf16 operands, fp32 accumulation in TMEM, TMA bulk copies, persistent CTAs with the layer's
+ * weights resident in shared memory.  Activations and their gradients are kept in HBM as bf16 in a
+ * packed tile layout  packed[tile][feature/8][vertex in tile (128)][8]  that is at once the
+ * tcgen05 no-swizzle K-major operand (forward, dX) and MN-major operand (dW = dZ^T H); see
+ * csrc/mlp_tc.cu.  Feature counts are padded: ep_tc_pad_features(d, wide) -> multiple of 32, or of
+ * 128 for hidden widths (wide = 1); padded sizes must be <= 256.  Padding is zero-filled. */
+EP_API int ep_tc_pad_features(int d, int wide);
+EP_API size_t ep_tc_packed_rows_bytes(int n, int d_padded);
+EP_API size_t ep_tc_packed_weight_bytes(int out_padded, int in_padded);
+/* fp32 rows [n x d] -> packed bf16 tiles (corrector input h; gradient w.r.t. the network output). */
+EP_API int ep_tc_pack_rows_bf16(int n, int d, int d_padded, const float* X, int ldx, void* packed,
+                         ep_stream_t stream);
+/* W fp32 [out x in] (nn.Linear layout) -> Wp [in_p/8][out_p][8] and, if WTp != NULL, WTp [out_p/8][in_p][8]. */
+EP_API int ep_tc_pack_weight_bf16(int out, int in, int out_padded, int in_padded, const float* W, void* Wp,
+                           void* WTp, ep_stream_t stream);
+/* hidden layer: out_packed = relu?(A W^T + b) */
+EP_API int ep_tc_linear_fwd_bf16(int n, int in_padded, int out, int out_padded, const void* A_packed, const void* Wp,
+                          const float* bias, int relu, void* out_packed, ep_stream_t stream);
+/* last layer: corr = A W^T + b as fp32 rows and, fused, U_pred = U_base + scale * corr
+ * (multigrid_model.py:243-245); U_base / U_pred may both be NULL. */
+EP_API int ep_tc_linear_final_bf16(int n, int in_padded, int out, int out_padded, const void* A_packed, const void* Wp,
+                            const float* bias, float* corr, int ldc, const float* U_base, float scale,
+                            const float* scale_dev, float* U_pred, int ldu, ep_stream_t stream);
+/* dZ_prev = (dZ W) * [act > 0]; act = saved activation of the previous layer (ReLU mask). */
+EP_API int ep_tc_linear_dx_bf16(int n, int out_padded, int in_padded, const void* dZ_packed, const void* WTp,
+                         const void* act_packed, void* dZprev_packed, ep_stream_t stream);
+/* dW = dZ^T act (fp32 [out x in]) and db = column sums of dZ; deterministic two-stage reduction. */
+EP_API size_t ep_tc_dw_workspace_bytes(void);
+EP_API int ep_tc_linear_dw_bf16(int n, int out, int in, int out_padded, int in_padded, const void* dZ_packed,
+                         const void* act_packed, float* dW, float* db, void* workspace, size_t workspace_bytes,
+                         ep_stream_t stream);
 
 /* ---- optimiser: clip_grad_norm_ + Adam(weight_decay) step, multigrid_model.py:218-220,259-260
  * Parameters / gradients / moments live in one flat fp32 buffer each.

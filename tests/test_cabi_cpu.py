@@ -20,7 +20,7 @@ def test_header_declares_entry_points():
     names = _declared()
     assert len(names) >= 35
     for must in ("ep_spmm2_csr_f32", "ep_eigen_partials_f32", "ep_fps_f64", "ep_voxel_select_f64",
-                 "ep_linear_fwd_f32", "ep_adam_clip_step_f32", "ep_mlp_tc_fwd"):
+                 "ep_linear_fwd_f32", "ep_adam_clip_step_f32", "ep_tc_linear_fwd_bf16"):
         assert must in names
 
 
