@@ -68,12 +68,14 @@ class Fp32Mlp:
         wmax = max(dims[1:-1]) if len(dims) > 2 else dims[0]
         self.dx = [torch.empty((n, wmax), dtype=torch.float32, device=device) for _ in range(2)]
 
-    def forward(self, h):
+    def forward(self, h, U_base=None, scale=0.0, U_pred=None):
         x = h
         L = len(self.p.W)
         for l in range(L):
             ops.linear_fwd(x, self.p.W[l], self.p.b[l], relu=(l < L - 1), out=self.acts[l])
             x = self.acts[l]
+        if U_pred is not None:
+            ops.axpy_out(U_base, x, scale, out=U_pred)
         return x                                    # corr_raw (n x k)
 
     def backward(self, h, d_out):
@@ -136,9 +138,7 @@ class TrainStepEngine:
         return self.cfg.corr_scale * min(1.0, epoch / self.cfg.ramp_epochs)
 
     def forward(self, scale):
-        corr = self.mlp.forward(self.h)
-        ops.axpy_out(self.U_base, corr, scale, out=self.U_pred)
-        return corr
+        return self.mlp.forward(self.h, U_base=self.U_base, scale=scale, U_pred=self.U_pred)
 
     def _level_slices(self, li):
         off, n = self.offsets[li], self.pairs[li].n

@@ -1,0 +1,101 @@
+"""bf16 tensor-core back end of the corrector MLP ("perf mode"): host-side buffer management around
+the tcgen05 kernels of csrc/mlp_tc.cu.  Same interface as engine.Fp32Mlp."""
+import ctypes
+
+import torch
+
+from ._cabi import call, query, EpError
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def pack_rows(X, d_padded=None, out=None):
+    """fp32 rows -> packed bf16 tiles [tile][d_p/8][128][8] (uint8 tensor)."""
+    n, d = X.shape
+    dp = d_padded if d_padded is not None else query("ep_tc_pad_features", d, 0)
+    nbytes = query("ep_tc_packed_rows_bytes", n, dp)
+    out = out if out is not None else torch.empty(nbytes, dtype=torch.uint8, device=X.device)
+    call("ep_tc_pack_rows_bf16", n, d, dp, _p(X), X.stride(0), _p(out), _stream())
+    return out
+
+
+def unpack_rows(packed, n, d_padded):
+    """Inverse of pack_rows for tests / debugging: (n, d_padded) fp32 tensor (torch ops, not a hot path)."""
+    tiles = (n + 127) // 128
+    t = packed.view(torch.bfloat16).view(tiles, d_padded // 8, 128, 8)
+    return t.permute(0, 2, 1, 3).reshape(tiles * 128, d_padded)[:n].float()
+
+
+class TcMlp:
+    def __init__(self, n, params, device, h=None):
+        self.p, self.n, self.dev = params, n, device
+        dims = params.dims                                    # [in, h1, ..., out]
+        L = len(dims) - 1
+        if L < 2:
+            raise EpError("bf16 mode needs at least one hidden layer")
+        self.L = L
+        self.dims = dims
+        self.pd = [query("ep_tc_pad_features", dims[0], 0)] + \
+                  [query("ep_tc_pad_features", d, 1) for d in dims[1:-1]] + [query("ep_tc_pad_features", dims[-1], 0)]
+        if max(self.pd) > 256:
+            raise EpError("bf16 mode supports layer widths up to 256 (got %s)" % (dims,))
+        u8 = dict(dtype=torch.uint8, device=device)
+        rows = lambda d: torch.zeros(query("ep_tc_packed_rows_bytes", n, d), **u8)
+        self.x0 = rows(self.pd[0])
+        self.acts = [rows(self.pd[l + 1]) for l in range(L - 1)]             # outputs of hidden layers
+        wmax = max(self.pd[1:-1])
+        self.dz = [rows(wmax) for _ in range(2)]
+        self.dz_out = rows(self.pd[-1])
+        self.Wp = [torch.zeros(query("ep_tc_packed_weight_bytes", self.pd[l + 1], self.pd[l]), **u8) for l in range(L)]
+        self.WTp = [torch.zeros_like(w) for w in self.Wp]
+        self.ws_bytes = query("ep_tc_dw_workspace_bytes")
+        self.ws = torch.empty(self.ws_bytes, **u8)
+        self.corr = torch.empty((n, dims[-1]), dtype=torch.float32, device=device)
+        self._packed_version = None
+        if h is not None:
+            self.input_changed(h)
+
+    def input_changed(self, h):
+        pack_rows(h, self.pd[0], out=self.x0)
+        self._packed_version = (h.data_ptr(), h._version)
+
+    def _pack_weights(self):
+        for l in range(self.L):
+            W = self.p.W[l]
+            call("ep_tc_pack_weight_bf16", W.shape[0], W.shape[1], self.pd[l + 1], self.pd[l], _p(W), _p(self.Wp[l]),
+                 _p(self.WTp[l]) if l > 0 else None, _stream())
+
+    def forward(self, h, U_base=None, scale=0.0, U_pred=None):
+        if self._packed_version != (h.data_ptr(), h._version):
+            self.input_changed(h)
+        self._pack_weights()
+        x = self.x0
+        for l in range(self.L - 1):
+            call("ep_tc_linear_fwd_bf16", self.n, self.pd[l], self.dims[l + 1], self.pd[l + 1], _p(x), _p(self.Wp[l]),
+                 _p(self.p.b[l]), 1, _p(self.acts[l]), _stream())
+            x = self.acts[l]
+        l = self.L - 1
+        call("ep_tc_linear_final_bf16", self.n, self.pd[l], self.dims[-1], self.pd[-1], _p(x), _p(self.Wp[l]),
+             _p(self.p.b[l]), _p(self.corr), self.corr.stride(0), _p(U_base), float(scale), None, _p(U_pred),
+             U_pred.stride(0) if U_pred is not None else 0, _stream())
+        return self.corr
+
+    def backward(self, h, d_out):
+        L = self.L
+        pack_rows(d_out, self.pd[-1], out=self.dz_out)
+        dz, dz_w = self.dz_out, self.pd[-1]
+        for l in range(L - 1, -1, -1):
+            act = self.acts[l - 1] if l > 0 else self.x0
+            call("ep_tc_linear_dw_bf16", self.n, self.dims[l + 1], self.dims[l], dz_w, self.pd[l], _p(dz), _p(act),
+                 _p(self.p.dW[l]), _p(self.p.db[l]), _p(self.ws), self.ws_bytes, _stream())
+            if l > 0:
+                nxt = self.dz[l & 1]
+                call("ep_tc_linear_dx_bf16", self.n, dz_w, self.pd[l], _p(dz), _p(self.WTp[l]), _p(act), _p(nxt),
+                     _stream())
+                dz, dz_w = nxt, self.pd[l]
