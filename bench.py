@@ -347,7 +347,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="icosphere1m", choices=sorted(WORKLOADS))
-    ap.add_argument("--mlp-mode", default=os.environ.get("EP_MLP_MODE", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--mlp-mode", default=os.environ.get("EP_MLP_MODE", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
