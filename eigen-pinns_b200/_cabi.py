@@ -41,7 +41,8 @@ SIGNATURES = {
     "ep_tc_packed_weight_bytes": (c_sz, [c_int, c_int]),
     "ep_tc_pack_rows_bf16": (c_int, [c_int, c_int, c_int, c_p, c_int, c_p, c_p]),
     "ep_tc_pack_weight_bf16": (c_int, [c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p]),
-    "ep_tc_linear_fwd_bf16": (c_int, [c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_int, c_p, c_p]),
+    "ep_tc_relu_mask_bytes": (c_sz, [c_int, c_int]),
+    "ep_tc_linear_fwd_bf16": (c_int, [c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_int, c_p, c_p, c_p]),
     "ep_tc_linear_final_bf16": (c_int, [c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_int, c_p, c_f, c_p,
                                         c_p, c_int, c_p]),
     "ep_tc_linear_dx_bf16": (c_int, [c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_p]),

@@ -133,7 +133,8 @@ struct LinearArgs {
   const float* bias; int n_bias;   // bias[0..n_bias) (columns beyond are padding) or NULL
   int relu;
   uint8_t* out_packed;       // MODE_HIDDEN / MODE_DX: [tile][N/8][128][8]
-  const uint8_t* mask_packed;// MODE_DX: activations whose sign pattern is the ReLU mask (same layout as out)
+  uint32_t* mask_out;        // MODE_HIDDEN: ReLU bit mask [row][N/32] (bit j of word w: activation 32w+j > 0), may be NULL
+  const uint32_t* mask_in;   // MODE_DX: the bit mask written by the forward pass of the previous layer
   float* corr; int ldc;      // MODE_FINAL: fp32 rows
   const float* U_base; float* U_pred; int ldu; float scale; const float* scale_dev;
   int n_rows, n_out;
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(LINEAR_THREADS, 1) tc_linear_kernel(LinearArgs
   uint64_t* bready = tempty + 2;         // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bready + 1);
   float* bias_s = reinterpret_cast<float*>(tmem_slot + 2);      // N floats
+  float* stage_f = bias_s + N;                                  // MODE_FINAL only: 4 x 32 x 33 floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -224,59 +226,71 @@ __global__ void __launch_bounds__(LINEAR_THREADS, 1) tc_linear_kernel(LinearArgs
     // epilogue: thread = one vertex row of the tile; TMEM lane quadrant = warp % 4
     const int q = warp & 3;
     const int r = q * 32 + lane;
+    const int ncb = N / 32;                              // 32-column blocks (<= 8)
     int acc = 0; uint32_t acc_phase = 0;
     const float scale = (MODE == MODE_FINAL && a.scale_dev) ? *a.scale_dev : a.scale;
+    float* stg = stage_f + (size_t)q * 32 * 33;           // MODE_FINAL: per-warp 32 x 33 transpose buffer
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      const long long row = (long long)tile * TILE_M + r;
+      uint32_t mw[8];
+      if (MODE == MODE_DX) {                              // ReLU mask of this row, fetched before the MMAs finish
+#pragma unroll
+        for (int w = 0; w < 8; ++w) mw[w] = (w < ncb) ? __ldg(a.mask_in + (size_t)row * ncb + w) : 0u;
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
       const size_t tile_off = (size_t)tile * (N / 8) * CHUNK_BYTES + (size_t)r * 16;
-      const long long row = (long long)tile * TILE_M + r;
-      for (int cb = 0; cb < N / 32; ++cb) {
-        uint32_t v[32];
-        tmem_ld32(t_addr + cb * 32, v);
-        if (MODE == MODE_FINAL) {
-          if (row < a.n_rows) {
-            float* c_row = a.corr + (size_t)row * a.ldc + cb * 32;
-            const float* u_row = a.U_base ? a.U_base + (size_t)row * a.ldu + cb * 32 : nullptr;
-            float* p_row = a.U_pred ? a.U_pred + (size_t)row * a.ldu + cb * 32 : nullptr;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = cb * 32 + j;
-              if (col < a.n_out) {
-                const float c = __uint_as_float(v[j]) + bias_s[col];
-                c_row[j] = c;
-                if (p_row) p_row[j] = __fadd_rn(u_row[j], __fmul_rn(scale, c));
+      for (int cb = 0; cb < 8; ++cb) {
+        if (cb < ncb) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + cb * 32, v);
+          if (MODE == MODE_FINAL) {
+            // transpose through shared memory so that every store instruction writes 128 contiguous bytes
+#pragma unroll
+            for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]) + bias_s[cb * 32 + j];
+            __syncwarp();
+            const int col = cb * 32 + lane;
+            const long long row0 = (long long)tile * TILE_M + q * 32;
+            if (col < a.n_out) {
+#pragma unroll 4
+              for (int rr = 0; rr < 32; ++rr) {
+                const long long grow = row0 + rr;
+                if (grow < a.n_rows) {
+                  const float c = stg[rr * 33 + lane];
+                  a.corr[(size_t)grow * a.ldc + col] = c;
+                  if (a.U_pred)
+                    a.U_pred[(size_t)grow * a.ldu + col] = __fadd_rn(__ldg(a.U_base + (size_t)grow * a.ldu + col), __fmul_rn(scale, c));
+                }
               }
             }
-          }
-        } else {
+            __syncwarp();
+          } else {
+            uint32_t bits = 0;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {                       // 4 chunks of 8 columns
-            const int c = cb * 4 + g;
-            float f[8];
+            for (int g = 0; g < 4; ++g) {                     // 4 chunks of 8 columns
+              const int c = cb * 4 + g;
+              float f[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-            if (MODE == MODE_HIDDEN) {
+              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+              if (MODE == MODE_HIDDEN) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                f[j] += bias_s[c * 8 + j];
-                if (a.relu) f[j] = fmaxf(f[j], 0.f);
+                for (int j = 0; j < 8; ++j) {
+                  f[j] += bias_s[c * 8 + j];
+                  if (a.relu) f[j] = fmaxf(f[j], 0.f);
+                  bits |= (f[j] > 0.f ? 1u : 0u) << (g * 8 + j);
+                }
+              } else {                                        // MODE_DX: keep where the forward activation was > 0
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = ((mw[cb] >> (g * 8 + j)) & 1u) ? f[j] : 0.f;
               }
-            } else {                                          // MODE_DX: keep where the saved activation is > 0
-              const uint4 m = __ldg(reinterpret_cast<const uint4*>(a.mask_packed + tile_off + (size_t)c * CHUNK_BYTES));
-              const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const uint32_t hbits = (mw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
-                const bool pos = (hbits != 0u) && ((hbits & 0x8000u) == 0u);
-                f[j] = pos ? f[j] : 0.f;
-              }
+              uint4 o;
+              o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+              o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+              *reinterpret_cast<uint4*>(a.out_packed + tile_off + (size_t)c * CHUNK_BYTES) = o;
             }
-            uint4 o;
-            o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-            o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-            *reinterpret_cast<uint4*>(a.out_packed + tile_off + (size_t)c * CHUNK_BYTES) = o;
+            if (MODE == MODE_HIDDEN && a.mask_out) a.mask_out[(size_t)row * ncb + cb] = bits;
           }
         }
       }
@@ -470,24 +484,41 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(DwArgs a) {
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
-// out[o][i] = sum_cta partial[cta][m][n], (m, n) = (o, i) or (i, o) when transposed
+// out[o][i] = sum_cta partial[cta][m][n], (m, n) = (o, i) or (i, o) when transposed.  64 outputs per block,
+// four thread groups split the CTA partials and are combined in a fixed order (deterministic).
 __global__ void __launch_bounds__(256)
 dw_reduce_kernel(int n_cta, int Mdim, int Ndim, const float* __restrict__ partial, int out_rows, int out_cols,
                  int transposed, float* __restrict__ dW, const float* __restrict__ db_partial, int db_len,
                  float* __restrict__ db) {
+  __shared__ float sh[4][64];
   const int total = out_rows * out_cols;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int el = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int e = blockIdx.x * 64 + el;
+  float s = 0.f;
   if (e < total) {
     const int o = e / out_cols, i = e - o * out_cols;
     const size_t idx = transposed ? (size_t)i * Ndim + o : (size_t)o * Ndim + i;
-    float s = 0.f;
-    for (int c = 0; c < n_cta; ++c) s += partial[(size_t)c * Mdim * Ndim + idx];
-    dW[e] = s;
+    const size_t stride = (size_t)Mdim * Ndim;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int c = g;
+    for (; c + 12 < n_cta; c += 16) {
+      s0 += partial[(size_t)c * stride + idx];
+      s1 += partial[(size_t)(c + 4) * stride + idx];
+      s2 += partial[(size_t)(c + 8) * stride + idx];
+      s3 += partial[(size_t)(c + 12) * stride + idx];
+    }
+    for (; c < n_cta; c += 4) s0 += partial[(size_t)c * stride + idx];
+    s = (s0 + s1) + (s2 + s3);
   }
-  if (e < db_len) {
-    float s = 0.f;
-    for (int c = 0; c < n_cta; ++c) s += db_partial[(size_t)c * 256 + e];
-    db[e] = s;
+  sh[g][el] = s;
+  __syncthreads();
+  if (g == 0 && e < total) dW[e] = (sh[0][el] + sh[1][el]) + (sh[2][el] + sh[3][el]);
+  if (blockIdx.x == 0) {
+    for (int f = threadIdx.x; f < db_len; f += blockDim.x) {
+      float t = 0.f;
+      for (int c = 0; c < n_cta; ++c) t += db_partial[(size_t)c * 256 + f];
+      db[f] = t;
+    }
   }
 }
 
@@ -495,14 +526,20 @@ dw_reduce_kernel(int n_cta, int Mdim, int Ndim, const float* __restrict__ partia
 // fp32 rows [n x d] -> packed bf16 tiles [tile][dp/8][128][8], zero padded (rows >= n, cols >= d)
 __global__ void __launch_bounds__(256)
 pack_rows_kernel(int n, int d, int dp, const float* __restrict__ X, int ldx, uint8_t* __restrict__ out, int n_tiles) {
-  const int nc = dp / 8;
-  const long long total = (long long)n_tiles * nc * TILE_M;           // one 16-byte chunk per item
+  // item = one 16-byte chunk.  A warp covers 8 rows x 4 chunks: reads are 128 contiguous bytes per row,
+  // writes 128 contiguous bytes per chunk column (8 rows x 16 B).
+  const int nc = dp / 8, ncg = nc / 4;                                // dp is a multiple of 32
+  const long long total = (long long)n_tiles * nc * TILE_M;
   for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total;
        it += (long long)gridDim.x * blockDim.x) {
-    const int r = (int)(it % TILE_M);
-    const long long tc_ = it / TILE_M;
-    const int c = (int)(tc_ % nc);
-    const long long tile = tc_ / nc;
+    const int lane = (int)(it & 31);
+    const long long w = it >> 5;
+    const int rg = (int)(w & 15);
+    const long long w2 = w >> 4;
+    const int cg = (int)(w2 % ncg);
+    const long long tile = w2 / ncg;
+    const int r = rg * 8 + (lane >> 2);
+    const int c = cg * 4 + (lane & 3);
     const long long row = tile * TILE_M + r;
     float f[8];
 #pragma unroll
@@ -513,7 +550,7 @@ pack_rows_kernel(int n, int d, int dp, const float* __restrict__ X, int ldx, uin
     uint4 o;
     o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
     o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-    *reinterpret_cast<uint4*>(out + (size_t)it * 16) = o;
+    *reinterpret_cast<uint4*>(out + (((size_t)tile * nc + c) * TILE_M + r) * 16) = o;
   }
 }
 
@@ -543,7 +580,7 @@ namespace {
 template <int MODE>
 int launch_linear(const LinearArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)a.KC * a.N * 16 + (size_t)N_STAGES * STAGE_BYTES + 8 * (2 * N_STAGES + 5) + 16 +
-                      sizeof(float) * a.N + 128;
+                      sizeof(float) * a.N + (MODE == MODE_FINAL ? sizeof(float) * 4 * 32 * 33 : 0) + 128;
   static size_t configured = 0;
   if (smem > configured) {
     EP_CUDA_CHECK(cudaFuncSetAttribute(tc_linear_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -571,8 +608,13 @@ size_t ep_tc_packed_rows_bytes(int n, int d_padded) {
 
 size_t ep_tc_packed_weight_bytes(int out_padded, int in_padded) { return (size_t)out_padded * in_padded * 2; }
 
+size_t ep_tc_relu_mask_bytes(int n, int d_padded) {
+  if (n <= 0 || d_padded <= 0) return 0;
+  return (size_t)n_tiles_for(n) * TILE_M * (d_padded / 32) * 4;
+}
+
 int ep_tc_pack_rows_bf16(int n, int d, int d_padded, const float* X, int ldx, void* packed, ep_stream_t stream) {
-  EP_REQUIRE(n > 0 && d > 0 && d_padded >= d && d_padded % 8 == 0, "bad size");
+  EP_REQUIRE(n > 0 && d > 0 && d_padded >= d && d_padded % 32 == 0, "bad size (d_padded must be a multiple of 32)");
   EP_REQUIRE(X && packed && ldx >= d, "bad argument");
   const int nt = n_tiles_for(n);
   const long long total = (long long)nt * (d_padded / 8) * TILE_M;
@@ -595,13 +637,14 @@ int ep_tc_pack_weight_bf16(int out, int in, int out_padded, int in_padded, const
 }
 
 int ep_tc_linear_fwd_bf16(int n, int in_padded, int out, int out_padded, const void* A_packed, const void* Wp,
-                          const float* bias, int relu, void* out_packed, ep_stream_t stream) {
+                          const float* bias, int relu, void* out_packed, void* relu_mask_out, ep_stream_t stream) {
   EP_REQUIRE(n > 0 && A_packed && Wp && out_packed, "bad argument");
   if (!dims_ok(in_padded, out_padded)) { ep::set_error("ep_tc_linear_fwd_bf16: padded dims must be multiples of 32 in [32, 256]"); return EP_ERR_UNSUPPORTED; }
   LinearArgs a{};
   a.A = static_cast<const uint8_t*>(A_packed); a.B = static_cast<const uint8_t*>(Wp);
   a.n_tiles = n_tiles_for(n); a.KC = in_padded / 8; a.N = out_padded; a.bias = bias; a.n_bias = out; a.relu = relu;
-  a.out_packed = static_cast<uint8_t*>(out_packed); a.n_rows = n; a.n_out = out_padded;
+  a.out_packed = static_cast<uint8_t*>(out_packed); a.mask_out = static_cast<uint32_t*>(relu_mask_out);
+  a.n_rows = n; a.n_out = out_padded;
   return launch_linear<MODE_HIDDEN>(a, ep::as_stream(stream));
 }
 
@@ -620,13 +663,13 @@ int ep_tc_linear_final_bf16(int n, int in_padded, int out, int out_padded, const
 }
 
 int ep_tc_linear_dx_bf16(int n, int out_padded, int in_padded, const void* dZ_packed, const void* WTp,
-                         const void* act_packed, void* dZprev_packed, ep_stream_t stream) {
-  EP_REQUIRE(n > 0 && dZ_packed && WTp && act_packed && dZprev_packed, "bad argument");
+                         const void* relu_mask, void* dZprev_packed, ep_stream_t stream) {
+  EP_REQUIRE(n > 0 && dZ_packed && WTp && relu_mask && dZprev_packed, "bad argument");
   if (!dims_ok(out_padded, in_padded)) { ep::set_error("ep_tc_linear_dx_bf16: unsupported dims"); return EP_ERR_UNSUPPORTED; }
   LinearArgs a{};
   a.A = static_cast<const uint8_t*>(dZ_packed); a.B = static_cast<const uint8_t*>(WTp);
   a.n_tiles = n_tiles_for(n); a.KC = out_padded / 8; a.N = in_padded;
-  a.out_packed = static_cast<uint8_t*>(dZprev_packed); a.mask_packed = static_cast<const uint8_t*>(act_packed);
+  a.out_packed = static_cast<uint8_t*>(dZprev_packed); a.mask_in = static_cast<const uint32_t*>(relu_mask);
   a.n_rows = n; a.n_out = in_padded;
   return launch_linear<MODE_DX>(a, ep::as_stream(stream));
 }
@@ -667,7 +710,7 @@ int ep_tc_linear_dw_bf16(int n, int out, int in, int out_padded, int in_padded, 
   tc_dw_kernel<<<grid, DW_THREADS, smem, st>>>(a);
   EP_LAUNCH_CHECK("tc_dw_kernel");
   const int total = out * in;
-  dw_reduce_kernel<<<ep::ceil_div(total > out ? total : out, 256), 256, 0, st>>>(
+  dw_reduce_kernel<<<ep::ceil_div(total, 64), 256, 0, st>>>(
       grid, a.Mdim, a.Ndim, a.partial, out, in, transposed, dW, a.db_partial, out, db);
   EP_LAUNCH_CHECK("dw_reduce_kernel");
   return EP_OK;

@@ -49,6 +49,7 @@ class TcMlp:
         rows = lambda d: torch.zeros(query("ep_tc_packed_rows_bytes", n, d), **u8)
         self.x0 = rows(self.pd[0])
         self.acts = [rows(self.pd[l + 1]) for l in range(L - 1)]             # outputs of hidden layers
+        self.masks = [torch.zeros(query("ep_tc_relu_mask_bytes", n, self.pd[l + 1]), **u8) for l in range(L - 1)]
         wmax = max(self.pd[1:-1])
         self.dz = [rows(wmax) for _ in range(2)]
         self.dz_out = rows(self.pd[-1])
@@ -78,7 +79,7 @@ class TcMlp:
         x = self.x0
         for l in range(self.L - 1):
             call("ep_tc_linear_fwd_bf16", self.n, self.pd[l], self.dims[l + 1], self.pd[l + 1], _p(x), _p(self.Wp[l]),
-                 _p(self.p.b[l]), 1, _p(self.acts[l]), _stream())
+                 _p(self.p.b[l]), 1, _p(self.acts[l]), _p(self.masks[l]), _stream())
             x = self.acts[l]
         l = self.L - 1
         call("ep_tc_linear_final_bf16", self.n, self.pd[l], self.dims[-1], self.pd[-1], _p(x), _p(self.Wp[l]),
@@ -96,6 +97,6 @@ class TcMlp:
                  _p(self.p.dW[l]), _p(self.p.db[l]), _p(self.ws), self.ws_bytes, _stream())
             if l > 0:
                 nxt = self.dz[l & 1]
-                call("ep_tc_linear_dx_bf16", self.n, dz_w, self.pd[l], _p(dz), _p(self.WTp[l]), _p(act), _p(nxt),
-                     _stream())
+                call("ep_tc_linear_dx_bf16", self.n, dz_w, self.pd[l], _p(dz), _p(self.WTp[l]), _p(self.masks[l - 1]),
+                     _p(nxt), _stream())
                 dz, dz_w = nxt, self.pd[l]

@@ -172,17 +172,20 @@ EP_API int ep_tc_pack_rows_bf16(int n, int d, int d_padded, const float* X, int 
 /* W fp32 [out x in] (nn.Linear layout) -> Wp [in_p/8][out_p][8] and, if WTp != NULL, WTp [out_p/8][in_p][8]. */
 EP_API int ep_tc_pack_weight_bf16(int out, int in, int out_padded, int in_padded, const float* W, void* Wp,
                            void* WTp, ep_stream_t stream);
-/* hidden layer: out_packed = relu?(A W^T + b) */
+/* hidden layer: out_packed = relu?(A W^T + b); relu_mask_out (may be NULL) receives one bit per
+ * activation, [row][out_padded/32] words, bit j of word w set iff activation 32w+j > 0. */
+EP_API size_t ep_tc_relu_mask_bytes(int n, int d_padded);
 EP_API int ep_tc_linear_fwd_bf16(int n, int in_padded, int out, int out_padded, const void* A_packed, const void* Wp,
-                          const float* bias, int relu, void* out_packed, ep_stream_t stream);
+                          const float* bias, int relu, void* out_packed, void* relu_mask_out,
+                          ep_stream_t stream);
 /* last layer: corr = A W^T + b as fp32 rows and, fused, U_pred = U_base + scale * corr
  * (multigrid_model.py:243-245); U_base / U_pred may both be NULL. */
 EP_API int ep_tc_linear_final_bf16(int n, int in_padded, int out, int out_padded, const void* A_packed, const void* Wp,
                             const float* bias, float* corr, int ldc, const float* U_base, float scale,
                             const float* scale_dev, float* U_pred, int ldu, ep_stream_t stream);
-/* dZ_prev = (dZ W) * [act > 0]; act = saved activation of the previous layer (ReLU mask). */
+/* dZ_prev = (dZ W) * [act > 0]; the ReLU mask of the previous layer is the bit mask its forward wrote. */
 EP_API int ep_tc_linear_dx_bf16(int n, int out_padded, int in_padded, const void* dZ_packed, const void* WTp,
-                         const void* act_packed, void* dZprev_packed, ep_stream_t stream);
+                         const void* relu_mask, void* dZprev_packed, ep_stream_t stream);
 /* dW = dZ^T act (fp32 [out x in]) and db = column sums of dZ; deterministic two-stage reduction. */
 EP_API size_t ep_tc_dw_workspace_bytes(void);
 EP_API int ep_tc_linear_dw_bf16(int n, int out, int in, int out_padded, int in_padded, const void* dZ_packed,

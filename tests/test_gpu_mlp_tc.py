@@ -47,13 +47,17 @@ def test_tc_hidden_forward(n, d_in, d_out):
     st = P(torch.cuda.current_stream().cuda_stream)
     _call("ep_tc_pack_weight_bf16", d_out, d_in, op, ip, P(W.data_ptr()), P(Wp.data_ptr()), None, st)
     out = torch.zeros(cabi.query("ep_tc_packed_rows_bytes", n, op), dtype=torch.uint8, device=dev())
+    mask = torch.zeros(cabi.query("ep_tc_relu_mask_bytes", n, op), dtype=torch.uint8, device=dev())
     _call("ep_tc_linear_fwd_bf16", n, ip, d_out, op, P(xp.data_ptr()), P(Wp.data_ptr()), P(b.data_ptr()), 1,
-          P(out.data_ptr()), st)
+          P(out.data_ptr()), P(mask.data_ptr()), st)
     torch.cuda.synchronize()
     got = tcm.unpack_rows(out, n, op)[:, :d_out]
     ref = torch.relu(bf(X).double() @ bf(W).double().t() + b.double()).float()
     err = (got - ref).abs().max().item()
     assert err <= 2.0 ** -7 * max(1.0, ref.abs().max().item()), err
+    words = mask.view(torch.int32).view(-1, op // 32)[:n]
+    bits = ((words.unsqueeze(-1) >> torch.arange(32, device=dev())) & 1).reshape(n, op)[:, :d_out]
+    assert torch.equal(bits.bool(), got > 0)
 
 
 def _mlp_pair(n, dims, seed=0):
