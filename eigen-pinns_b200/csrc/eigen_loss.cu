@@ -20,34 +20,44 @@ inline int partial_blocks(int n, int rows_per_tile) {
   return g < 1 ? 1 : g;
 }
 
-// TG x TG register block of the Gram matrix per thread, 16 x 16 threads -> KP = 16 TG columns.
-template <int TG>
+// Gram / column-sum partials.  KP = padded column count; each thread owns a TG x TG block of the Gram
+// matrix, (KP/TG)^2 threads form a sub-group and the 256 / (KP/TG)^2 sub-groups take alternate rows of the
+// tile, so every FMA group costs two 16-byte shared-memory reads (TG = 4: 16 FMA per 2 LDS.128).
+template <int KP, int TG>
 __global__ void __launch_bounds__(kPartialThreads)
 eigen_partials_kernel(int n, int k, const float* __restrict__ U, int ldu, const float* __restrict__ KU,
                       const float* __restrict__ MU, int ld, double* __restrict__ block_out) {
-  constexpr int KP = 16 * TG;
-  constexpr int R = (TG == 8) ? 16 : 32;        // rows per tile (3 tiles must fit 48 KB static smem)
-  constexpr int CPL = (KP + 31) / 32;           // columns per lane for the column sums
+  constexpr int TPD = KP / TG;
+  constexpr int NT = TPD * TPD;
+  constexpr int NSG = kPartialThreads / NT;
+  constexpr int R = (KP == 128) ? 16 : 32;
+  constexpr int CPL = (KP + 31) / 32;
+  constexpr int FLUSH = 4;                       // fold fp32 -> fp64 every FLUSH tiles
+  static_assert(NT * NSG == kPartialThreads && NSG >= 1, "bad tiling");
   __shared__ __align__(16) float Us[R][KP];
   __shared__ __align__(16) float KUs[R][KP];
   __shared__ __align__(16) float MUs[R][KP];
+  __shared__ double red[(NSG > 1) ? KP * KP : 8 * KP];
 
   const int tid = threadIdx.x;
-  const int ty = tid >> 4, tx = tid & 15;
+  const int sg = tid / NT, tin = tid % NT;
+  const int ty = tin / TPD, tx = tin % TPD;
   const int warp = tid >> 5, lane = tid & 31;
 
   double g64[TG][TG];
+  float g32[TG][TG];
   double c64[4][CPL];
 #pragma unroll
   for (int i = 0; i < TG; ++i)
 #pragma unroll
-    for (int j = 0; j < TG; ++j) g64[i][j] = 0.0;
+    for (int j = 0; j < TG; ++j) { g64[i][j] = 0.0; g32[i][j] = 0.f; }
 #pragma unroll
   for (int q = 0; q < 4; ++q)
 #pragma unroll
     for (int c = 0; c < CPL; ++c) c64[q][c] = 0.0;
 
   const int n_tiles = (n + R - 1) / R;
+  int since_flush = 0;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int row0 = tile * R;
     __syncthreads();
@@ -60,28 +70,28 @@ eigen_partials_kernel(int n, int k, const float* __restrict__ U, int ldu, const 
       MUs[r][c] = ok ? __ldg(MU + (size_t)row * ld + c) : 0.f;
     }
     __syncthreads();
-    // Gram block: G[ty*TG+i][tx*TG+j] += U[r][ty*TG+i] * MU[r][tx*TG+j]
-    float g32[TG][TG];
-#pragma unroll
-    for (int i = 0; i < TG; ++i)
-#pragma unroll
-      for (int j = 0; j < TG; ++j) g32[i][j] = 0.f;
-#pragma unroll 4
-    for (int r = 0; r < R; ++r) {
+#pragma unroll 2
+    for (int r = sg; r < R; r += NSG) {
       float a[TG], b[TG];
 #pragma unroll
-      for (int i = 0; i < TG; ++i) a[i] = Us[r][ty * TG + i];
-#pragma unroll
-      for (int j = 0; j < TG; ++j) b[j] = MUs[r][tx * TG + j];
+      for (int i = 0; i < TG; i += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(&Us[r][ty * TG + i]);
+        a[i] = t.x; a[i + 1] = t.y; a[i + 2] = t.z; a[i + 3] = t.w;
+        const float4 u = *reinterpret_cast<const float4*>(&MUs[r][tx * TG + i]);
+        b[i] = u.x; b[i + 1] = u.y; b[i + 2] = u.z; b[i + 3] = u.w;
+      }
 #pragma unroll
       for (int i = 0; i < TG; ++i)
 #pragma unroll
         for (int j = 0; j < TG; ++j) g32[i][j] = fmaf(a[i], b[j], g32[i][j]);
     }
+    if (++since_flush == FLUSH) {
+      since_flush = 0;
 #pragma unroll
-    for (int i = 0; i < TG; ++i)
+      for (int i = 0; i < TG; ++i)
 #pragma unroll
-      for (int j = 0; j < TG; ++j) g64[i][j] += (double)g32[i][j];
+        for (int j = 0; j < TG; ++j) { g64[i][j] += (double)g32[i][j]; g32[i][j] = 0.f; }
+    }
     // column sums: warp w owns rows w, w+8, ...; lane owns columns lane, lane+32, ...
 #pragma unroll
     for (int cc = 0; cc < CPL; ++cc) {
@@ -100,19 +110,41 @@ eigen_partials_kernel(int n, int k, const float* __restrict__ U, int ldu, const 
       }
     }
   }
-  // ---- write this block's partials: Gram directly, column sums reduced over the 8 warps
-  double* out = block_out + (size_t)blockIdx.x * partials_len(k);
 #pragma unroll
   for (int i = 0; i < TG; ++i)
 #pragma unroll
-    for (int j = 0; j < TG; ++j) {
-      const int a = ty * TG + i, b = tx * TG + j;
-      if (a < k && b < k) out[a * k + b] = g64[i][j];
+    for (int j = 0; j < TG; ++j) g64[i][j] += (double)g32[i][j];
+
+  double* out = block_out + (size_t)blockIdx.x * partials_len(k);
+  if (NSG > 1) {                                  // combine the row sub-groups in a fixed order
+    for (int s2 = 0; s2 < NSG; ++s2) {
+      __syncthreads();
+      if (sg == s2) {
+#pragma unroll
+        for (int i = 0; i < TG; ++i)
+#pragma unroll
+          for (int j = 0; j < TG; ++j) {
+            const int idx = (ty * TG + i) * KP + tx * TG + j;
+            red[idx] = (s2 == 0) ? g64[i][j] : red[idx] + g64[i][j];
+          }
+      }
     }
-  __syncthreads();
-  double* red = reinterpret_cast<double*>(&Us[0][0]);       // 8 warps x KP doubles fit in the U tile
-  static_assert(sizeof(double) * 8 * KP <= sizeof(float) * R * KP, "reduction scratch too small");
+    __syncthreads();
+    for (int e = tid; e < KP * KP; e += kPartialThreads) {
+      const int a_ = e / KP, b_ = e - a_ * KP;
+      if (a_ < k && b_ < k) out[a_ * k + b_] = red[e];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < TG; ++i)
+#pragma unroll
+      for (int j = 0; j < TG; ++j) {
+        const int a_ = ty * TG + i, b_ = tx * TG + j;
+        if (a_ < k && b_ < k) out[a_ * k + b_] = g64[i][j];
+      }
+  }
   for (int q = 0; q < 4; ++q) {
+    __syncthreads();
 #pragma unroll
     for (int cc = 0; cc < CPL; ++cc) {
       const int c = lane + 32 * cc;
@@ -124,17 +156,27 @@ eigen_partials_kernel(int n, int k, const float* __restrict__ U, int ldu, const 
       for (int w = 0; w < kPartialThreads / 32; ++w) s += red[w * KP + tid];
       out[k * k + q * k + tid] = s;
     }
-    __syncthreads();
   }
 }
 
+// sum of the per-block partials: 64 outputs per block, 4 thread groups over the blocks, fixed order
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(int n_blocks, int len, const double* __restrict__ block_out, double* __restrict__ out) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= len) return;
-  double s = 0.0;
-  for (int b = 0; b < n_blocks; ++b) s += block_out[(size_t)b * len + e];
-  out[e] = s;
+  __shared__ double sh[4][64];
+  const int el = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int e = blockIdx.x * 64 + el;
+  double s0 = 0.0, s1 = 0.0;
+  if (e < len) {
+    int b = g;
+    for (; b + 4 < n_blocks; b += 8) {
+      s0 += block_out[(size_t)b * len + e];
+      s1 += block_out[(size_t)(b + 4) * len + e];
+    }
+    for (; b < n_blocks; b += 4) s0 += block_out[(size_t)b * len + e];
+  }
+  sh[g][el] = s0 + s1;
+  __syncthreads();
+  if (g == 0 && e < len) out[e] = (sh[0][el] + sh[1][el]) + (sh[2][el] + sh[3][el]);
 }
 
 __device__ double block_sum_256(double v, double* scratch) {
@@ -324,6 +366,109 @@ eigen_bwd_prepare_kernel(int n, int k, const float* __restrict__ U, int ldu, con
   }
 }
 
+// Fused backward for SYMMETRIC K, M (FEM and tufted Laplacians):
+//   dU_i = s [ c sum_j (K_ij - lam M_ij) (KU_j - lam MU_j) + 2 a KU_i + MU_i S ],  S = Gp + Gp^T
+// (uses K (U diag a) = KU diag a and M (U Gp) = MU Gp, so neither KU_bar / MU_bar / D nor a second
+// k x k product is materialised).  One gather pass over the CSR pattern: reads the pattern, KU, MU once,
+// writes dU once -> 12 nnz + 4 (n+1) + 12 n k bytes, like the forward dual SpMM.
+// Thread layout as in the SpMM: LPR lanes per row, 4 columns per lane; the k x k product takes the row's
+// MU values from the other lanes with shuffles and S from shared memory.
+__global__ void __launch_bounds__(256)
+eigen_bwd_fused_sym_kernel(int n, int k, int lpr_shift, const int32_t* __restrict__ rowptr,
+                           const int32_t* __restrict__ col, const float* __restrict__ valK,
+                           const float* __restrict__ valM, const float* __restrict__ KU,
+                           const float* __restrict__ MU, int ld, const float* __restrict__ coef, float out_scale,
+                           float* __restrict__ dU, int ldo) {
+  extern __shared__ __align__(16) float fsm[];
+  float* S = fsm;                 // k x k
+  float* s_lam = S + k * k;       // k
+  float* s_a2 = s_lam + k;        // k
+  const float c_res = coef[0];
+  const float* c_lam = coef + 1;
+  const float* c_num = c_lam + k;
+  const float* c_den = c_num + k;
+  const float* c_G = c_den + k;
+  for (int e = threadIdx.x; e < k * k; e += blockDim.x) {
+    const int m = e / k, j = e - m * k;
+    float v = c_G[e] + c_G[j * k + m];
+    if (m == j) v += 2.f * c_den[m];
+    S[e] = v;
+  }
+  for (int e = threadIdx.x; e < k; e += blockDim.x) { s_lam[e] = c_lam[e]; s_a2[e] = 2.f * c_num[e]; }
+  __syncthreads();
+
+  const int lpr = 1 << lpr_shift;
+  const int kv = k >> 2;
+  const int lane_r = threadIdx.x & (lpr - 1);
+  const bool active = lane_r < kv;
+  const int cofs = active ? 4 * lane_r : 0;
+  const float4 lam4 = *reinterpret_cast<const float4*>(s_lam + cofs);
+  const float4 a24 = *reinterpret_cast<const float4*>(s_a2 + cofs);
+  const long long groups_per_grid = ((long long)gridDim.x * blockDim.x) >> lpr_shift;
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> lpr_shift;
+       row < (long long)((n + groups_per_grid - 1) / groups_per_grid) * groups_per_grid; row += groups_per_grid) {
+    const bool valid = row < n;
+    const int start = valid ? __ldg(rowptr + row) : 0;
+    const int end = valid ? __ldg(rowptr + row + 1) : 0;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) {
+      for (int j = start; j < end; j += 4) {
+        int c[4]; float kk[4], mm[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool ok = (j + u) < end;
+          c[u] = ok ? __ldg(col + j + u) : -1;
+          kk[u] = ok ? __ldg(valK + j + u) : 0.f;
+          mm[u] = ok ? __ldg(valM + j + u) : 0.f;
+        }
+        float4 ku[4], mu[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (c[u] >= 0) {
+            ku[u] = __ldg(reinterpret_cast<const float4*>(KU + (size_t)c[u] * ld + cofs));
+            mu[u] = __ldg(reinterpret_cast<const float4*>(MU + (size_t)c[u] * ld + cofs));
+          } else { ku[u] = make_float4(0.f, 0.f, 0.f, 0.f); mu[u] = ku[u]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          acc.x = fmaf(kk[u] - lam4.x * mm[u], ku[u].x - lam4.x * mu[u].x, acc.x);
+          acc.y = fmaf(kk[u] - lam4.y * mm[u], ku[u].y - lam4.y * mu[u].y, acc.y);
+          acc.z = fmaf(kk[u] - lam4.z * mm[u], ku[u].z - lam4.z * mu[u].z, acc.z);
+          acc.w = fmaf(kk[u] - lam4.w * mm[u], ku[u].w - lam4.w * mu[u].w, acc.w);
+        }
+      }
+    }
+    acc.x *= c_res; acc.y *= c_res; acc.z *= c_res; acc.w *= c_res;
+    float4 mu_i = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active && valid) {
+      const float4 ku_i = __ldg(reinterpret_cast<const float4*>(KU + (size_t)row * ld + cofs));
+      mu_i = __ldg(reinterpret_cast<const float4*>(MU + (size_t)row * ld + cofs));
+      acc.x = fmaf(a24.x, ku_i.x, acc.x); acc.y = fmaf(a24.y, ku_i.y, acc.y);
+      acc.z = fmaf(a24.z, ku_i.z, acc.z); acc.w = fmaf(a24.w, ku_i.w, acc.w);
+    }
+    // acc += MU_i S : lane L of the row group holds MU_i[4L .. 4L+3]
+    for (int L = 0; L < kv; ++L) {
+      const float m0 = __shfl_sync(0xffffffffu, mu_i.x, L, lpr);
+      const float m1 = __shfl_sync(0xffffffffu, mu_i.y, L, lpr);
+      const float m2 = __shfl_sync(0xffffffffu, mu_i.z, L, lpr);
+      const float m3 = __shfl_sync(0xffffffffu, mu_i.w, L, lpr);
+      const float* Sr = S + (size_t)(4 * L) * k + cofs;
+      const float4 s0 = *reinterpret_cast<const float4*>(Sr);
+      const float4 s1 = *reinterpret_cast<const float4*>(Sr + k);
+      const float4 s2 = *reinterpret_cast<const float4*>(Sr + 2 * k);
+      const float4 s3 = *reinterpret_cast<const float4*>(Sr + 3 * k);
+      acc.x = fmaf(m0, s0.x, acc.x); acc.y = fmaf(m0, s0.y, acc.y); acc.z = fmaf(m0, s0.z, acc.z); acc.w = fmaf(m0, s0.w, acc.w);
+      acc.x = fmaf(m1, s1.x, acc.x); acc.y = fmaf(m1, s1.y, acc.y); acc.z = fmaf(m1, s1.z, acc.z); acc.w = fmaf(m1, s1.w, acc.w);
+      acc.x = fmaf(m2, s2.x, acc.x); acc.y = fmaf(m2, s2.y, acc.y); acc.z = fmaf(m2, s2.z, acc.z); acc.w = fmaf(m2, s2.w, acc.w);
+      acc.x = fmaf(m3, s3.x, acc.x); acc.y = fmaf(m3, s3.y, acc.y); acc.z = fmaf(m3, s3.z, acc.z); acc.w = fmaf(m3, s3.w, acc.w);
+    }
+    if (active && valid) {
+      acc.x *= out_scale; acc.y *= out_scale; acc.z *= out_scale; acc.w *= out_scale;
+      *reinterpret_cast<float4*>(dU + (size_t)row * ldo + cofs) = acc;
+    }
+  }
+}
+
 template <int KP>
 int launch_bwd_prepare(int n, int k, const float* U, int ldu, const float* KU, const float* MU, int ld,
                        const float* coef, float* KU_bar, float* MU_bar, float* D, cudaStream_t st) {
@@ -391,22 +536,19 @@ int ep_eigen_partials_f32(int n, int k, const float* U, int ldu, const float* KU
   EP_REQUIRE(ldu >= k && ld >= k, "leading dimension < k");
   cudaStream_t st = ep::as_stream(stream);
   const int len = partials_len(k);
-  const int tg = k <= 16 ? 1 : k <= 32 ? 2 : k <= 64 ? 4 : 8;
-  const int rows = tg == 8 ? 16 : 32;
+  const int rows = k > 64 ? 16 : 32;
   const int grid = partial_blocks(n, rows);
   if (workspace_bytes < sizeof(double) * (size_t)len * grid) {
     ep::set_error("ep_eigen_partials_f32: workspace too small");
     return EP_ERR_WORKSPACE;
   }
   double* blocks = static_cast<double*>(workspace);
-  switch (tg) {
-    case 1: eigen_partials_kernel<1><<<grid, kPartialThreads, 0, st>>>(n, k, U, ldu, KU, MU, ld, blocks); break;
-    case 2: eigen_partials_kernel<2><<<grid, kPartialThreads, 0, st>>>(n, k, U, ldu, KU, MU, ld, blocks); break;
-    case 4: eigen_partials_kernel<4><<<grid, kPartialThreads, 0, st>>>(n, k, U, ldu, KU, MU, ld, blocks); break;
-    default: eigen_partials_kernel<8><<<grid, kPartialThreads, 0, st>>>(n, k, U, ldu, KU, MU, ld, blocks); break;
-  }
+  if (k <= 16)      eigen_partials_kernel<16, 4><<<grid, kPartialThreads, 0, st>>>(n, k, U, ldu, KU, MU, ld, blocks);
+  else if (k <= 32) eigen_partials_kernel<32, 4><<<grid, kPartialThreads, 0, st>>>(n, k, U, ldu, KU, MU, ld, blocks);
+  else if (k <= 64) eigen_partials_kernel<64, 4><<<grid, kPartialThreads, 0, st>>>(n, k, U, ldu, KU, MU, ld, blocks);
+  else              eigen_partials_kernel<128, 8><<<grid, kPartialThreads, 0, st>>>(n, k, U, ldu, KU, MU, ld, blocks);
   EP_LAUNCH_CHECK("eigen_partials_kernel");
-  reduce_partials_kernel<<<ep::ceil_div(len, 256), 256, 0, st>>>(grid, len, blocks, out);
+  reduce_partials_kernel<<<ep::ceil_div(len, 64), 256, 0, st>>>(grid, len, blocks, out);
   EP_LAUNCH_CHECK("reduce_partials_kernel");
   return EP_OK;
 }
@@ -436,6 +578,36 @@ int ep_eigen_bwd_prepare_f32(int n, int k, const float* U, int ldu, const float*
   if (k <= 32) return launch_bwd_prepare<32>(n, k, U, ldu, KU, MU, ld, coef, KU_bar, MU_bar, D, st);
   if (k <= 64) return launch_bwd_prepare<64>(n, k, U, ldu, KU, MU, ld, coef, KU_bar, MU_bar, D, st);
   return launch_bwd_prepare<128>(n, k, U, ldu, KU, MU, ld, coef, KU_bar, MU_bar, D, st);
+}
+
+int ep_eigen_bwd_fused_sym_f32(int n, int k, const int32_t* rowptr, const int32_t* col, const float* valK,
+                               const float* valM, const float* KU, const float* MU, int ld, const float* coef,
+                               float out_scale, float* dU, int ldo, ep_stream_t stream) {
+  EP_REQUIRE(n >= 0 && k > 0, "bad size");
+  if (n == 0) return EP_OK;
+  EP_REQUIRE(rowptr && col && valK && valM && KU && MU && coef && dU, "null pointer");
+  if (k % 4 != 0 || k > 128 || ld % 4 != 0 || ldo % 4 != 0 || !ep::aligned16(KU) || !ep::aligned16(MU) ||
+      !ep::aligned16(dU)) {
+    ep::set_error("ep_eigen_bwd_fused_sym_f32: needs k %% 4 == 0, k <= 128 and 16-byte aligned rows");
+    return EP_ERR_UNSUPPORTED;
+  }
+  const int kv = k / 4;
+  int lpr_shift = 0;
+  while ((1 << lpr_shift) < kv) ++lpr_shift;
+  const size_t smem = sizeof(float) * ((size_t)k * k + 2 * k);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    EP_CUDA_CHECK(cudaFuncSetAttribute(eigen_bwd_fused_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const long long threads = (long long)n << lpr_shift;
+  long long grid = (threads + 255) / 256;
+  const long long cap = (long long)ep::sm_count() * 8;
+  if (grid > cap) grid = cap;
+  eigen_bwd_fused_sym_kernel<<<(unsigned)grid, 256, smem, ep::as_stream(stream)>>>(
+      n, k, lpr_shift, rowptr, col, valK, valM, KU, MU, ld, coef, out_scale, dU, ldo);
+  EP_LAUNCH_CHECK("eigen_bwd_fused_sym_kernel");
+  return EP_OK;
 }
 
 int ep_scale_columns_rsqrt_f32(int n, int k, const float* U, int ldu, const double* G, int ldg, double eps,

@@ -132,6 +132,7 @@ class TrainStepEngine:
         else:
             raise ValueError("mlp_mode must be 'fp32' or 'bf16'")
         self.launches_per_step = None
+        self.fused_bwd = True          # symmetric operators: one-pass analytic backward
 
     # ---- pieces (also used one by one by the tests)
     def scale_for(self, epoch):
@@ -159,6 +160,9 @@ class TrainStepEngine:
     def loss_backward(self, scale):
         for li, pair in enumerate(self.pairs):
             s = self._level_slices(li)
+            if self.fused_bwd and ops.eigen_bwd_fused_ok(pair, self.k, self.KU[s], self.MU[s], self.dCorr[s]):
+                ops.eigen_bwd_fused(pair, self.KU[s], self.MU[s], self.coefs[li], scale, self.dCorr[s])
+                continue
             ops.eigen_bwd_prepare(self.U_pred[s], self.KU[s], self.MU[s], self.coefs[li], self.KU_bar[s],
                                   self.MU_bar[s], self.D[s])
             ops.spmm2_sum(pair.KT, pair.MT, self.KU_bar[s], self.MU_bar[s], self.D[s], scale, out=self.dCorr[s])

@@ -164,6 +164,20 @@ def eigen_bwd_prepare(U, KU, MU, coef, KU_bar=None, MU_bar=None, D=None):
     return KU_bar, MU_bar, D
 
 
+def eigen_bwd_fused_ok(pair, k, *tensors):
+    return (pair.symmetric and k % 4 == 0 and k <= 128
+            and all(t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in tensors))
+
+
+def eigen_bwd_fused(pair, KU, MU, coef, scale, out):
+    """dL/dU for symmetric (K, M) in one gather pass (see ep_eigen_bwd_fused_sym_f32)."""
+    n, k = KU.shape
+    assert KU.stride(0) == MU.stride(0)
+    call("ep_eigen_bwd_fused_sym_f32", n, k, _ptr(pair.K.rowptr), _ptr(pair.K.col), _ptr(pair.K.val), _ptr(pair.M.val),
+         _ptr(KU), _ptr(MU), KU.stride(0), _ptr(coef), float(scale), _ptr(out), out.stride(0), _stream())
+    return out
+
+
 def m_normalize_columns(U, M: CsrMatrix, eps=1e-12):
     """u_j / sqrt(u_j^T M u_j + eps); reference src/multigrid_model.py:120-130."""
     U = _check(_rowmajor(U))
@@ -234,8 +248,12 @@ class _EigenLossFn(torch.autograd.Function):
             U = U_pred[off:off + pair.n]
             extra = g_lams[li].contiguous() if (li < len(g_lams) and g_lams[li] is not None) else None
             _, coef = eigen_finalize(k, pair.n, P, w_res * gr, w_orth * go, scratch_acc, lam_bar_extra=extra)
-            KU_bar, MU_bar, D = eigen_bwd_prepare(U, KU, MU, coef)
-            spmm2_sum(pair.KT, pair.MT, KU_bar, MU_bar, D, 1.0, out=dU[off:off + pair.n])
+            dst = dU[off:off + pair.n]
+            if eigen_bwd_fused_ok(pair, k, KU, MU, dst):
+                eigen_bwd_fused(pair, KU, MU, coef, 1.0, dst)
+            else:
+                KU_bar, MU_bar, D = eigen_bwd_prepare(U, KU, MU, coef)
+                spmm2_sum(pair.KT, pair.MT, KU_bar, MU_bar, D, 1.0, out=dst)
         return dU, None, None, None, None
 
 

@@ -129,6 +129,14 @@ EP_API int ep_eigen_bwd_prepare_f32(int n, int k, const float* U, int ldu, const
                              int ld, const float* coef, float* KU_bar, float* MU_bar, float* D,
                              ep_stream_t stream);
 
+/* Phase 3, fused variant for SYMMETRIC K and M (one gather pass, nothing materialised):
+ *   dU = out_scale * [ c_res * sum_j (K_ij - lam M_ij)(KU_j - lam MU_j) + 2 num_bar KU_i + MU_i (Gp + Gp^T) ]
+ * with Gp = G_bar + diag(den_bar).  Algebraically equal to prepare + ep_spmm2_sum_csr_f32 when K = K^T,
+ * M = M^T.  Needs k % 4 == 0, k <= 128, 16-byte aligned rows (EP_ERR_UNSUPPORTED otherwise). */
+EP_API int ep_eigen_bwd_fused_sym_f32(int n, int k, const int32_t* rowptr, const int32_t* col, const float* valK,
+                               const float* valM, const float* KU, const float* MU, int ld, const float* coef,
+                               float out_scale, float* dU, int ldo, ep_stream_t stream);
+
 /* ---- column M-normalisation: multigrid_model.py:120-130, :366-380 ----------------------
  * out[:, j] = U[:, j] / sqrt(colsum_j + 1e-12) where colsum_j = sum_i U_ij MU_ij is read from
  * the diagonal of a partials block (G_jj).  */

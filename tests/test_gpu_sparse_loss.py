@@ -175,3 +175,35 @@ def test_large_mesh_properties():
     K1, M1 = ops.spmm2(pair, ones)
     assert K1.abs().max().item() < 2e-2 * float(abs(K).max())
     assert M1[:, 0].double().sum().item() == pytest.approx(8.0 * np.pi, rel=1e-4)
+
+
+@pytest.mark.parametrize("k", [16, 32, 64, 128])
+def test_fused_symmetric_backward_equals_general_path(k):
+    """One-pass backward (symmetric K, M) against prepare + transposed dual SpMM, and partials for every tiling."""
+    ops, sparse, engine = pkg("ops"), pkg("sparse"), pkg("engine")
+    fem, (K, M), _ = bunny_levels()
+    pair = sparse.OperatorPair(K, M, dev())
+    n = K.shape[0]
+    g = torch.Generator().manual_seed(k)
+    U = (0.3 * torch.randn(n, k, generator=g)).to(dev())
+    cfg = engine.StepConfig(w_trace=0.5, w_order=2.0, w_eigen=3.0)
+    outs = []
+    for fused in (True, False):
+        eng = engine.TrainStepEngine(torch.zeros(n, 4, device=dev()), U, [pair], [0],
+                                     engine.FlatParams([torch.zeros(k, 4)], [torch.zeros(k)], dev()), cfg,
+                                     lam_target=torch.linspace(0, 2, k).to(dev()))
+        eng.fused_bwd = fused
+        eng.U_pred.copy_(U)
+        eng.loss_forward()
+        eng.loss_backward(0.7)
+        outs.append((eng.dCorr.clone(), eng.loss_acc.clone()))
+    assert torch.equal(outs[0][1], outs[1][1])
+    ref = outs[1][0]
+    assert (outs[0][0] - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    # and against torch autograd on the CPU oracle
+    Uc = U.cpu().requires_grad_(True)
+    l_res, l_orth, lams = step_port.residual_ortho_loss(Uc, [K], [M], [0], cfg.w_res, cfg.w_orth, k)
+    extra = step_port.eigenvalue_losses(lams[0], torch.linspace(0, 2, k), 0.0, 0.5, 2.0, 3.0)
+    (l_res + l_orth + sum(extra)).backward()
+    gref = 0.7 * Uc.grad
+    assert (outs[0][0].cpu() - gref).abs().max().item() <= 5e-5 * gref.abs().max().item()
