@@ -241,9 +241,20 @@ __global__ void __launch_bounds__(LINEAR_THREADS, 1) tc_linear_kernel(LinearArgs
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
       const size_t tile_off = (size_t)tile * (N / 8) * CHUNK_BYTES + (size_t)r * 16;
+      const int cb_end = (MODE == MODE_FINAL) ? ncb : 8;     // FINAL: runtime bound, not unrolled (register budget)
 #pragma unroll
-      for (int cb = 0; cb < 8; ++cb) {
+      for (int cb = 0; cb < cb_end; ++cb) {
         if (cb < ncb) {
+          float ub[32];
+          if (MODE == MODE_FINAL) {
+            // U_base rows of this warp's 32 x 32 block, fetched (coalesced, all in flight) before the accumulator is read
+            const int col = cb * 32 + lane;
+            const long long row0 = (long long)tile * TILE_M + q * 32;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr)
+              ub[rr] = (a.U_base && col < a.n_out && row0 + rr < a.n_rows)
+                           ? __ldg(a.U_base + (size_t)(row0 + rr) * a.ldu + col) : 0.f;
+          }
           uint32_t v[32];
           tmem_ld32(t_addr + cb * 32, v);
           if (MODE == MODE_FINAL) {
@@ -254,14 +265,13 @@ __global__ void __launch_bounds__(LINEAR_THREADS, 1) tc_linear_kernel(LinearArgs
             const int col = cb * 32 + lane;
             const long long row0 = (long long)tile * TILE_M + q * 32;
             if (col < a.n_out) {
-#pragma unroll 4
+#pragma unroll
               for (int rr = 0; rr < 32; ++rr) {
                 const long long grow = row0 + rr;
                 if (grow < a.n_rows) {
                   const float c = stg[rr * 33 + lane];
                   a.corr[(size_t)grow * a.ldc + col] = c;
-                  if (a.U_pred)
-                    a.U_pred[(size_t)grow * a.ldu + col] = __fadd_rn(__ldg(a.U_base + (size_t)grow * a.ldu + col), __fmul_rn(scale, c));
+                  if (a.U_pred) a.U_pred[(size_t)grow * a.ldu + col] = __fadd_rn(ub[rr], __fmul_rn(scale, c));
                 }
               }
             }

@@ -1,0 +1,129 @@
+"""Vertex-sharded training step: one process per GPU, torch.distributed (NCCL over NVLink) for the
+three exchanges the path really has:
+
+  1. halo rows of U_pred before K U / M U, and of KU, MU before the backward gather
+     (point-to-point, only between ranks whose vertex ranges touch);
+  2. all-reduce (sum) of the packed fp64 partials [G | num | sKK | sKM | sMM] per level  -> global
+     Rayleigh quotients, residual and Gram terms; every rank then finalises identically;
+  3. all-reduce (sum) of the flat weight-gradient buffer before clip + Adam.
+
+Row space of a rank, per level:  [owned rows | halo rows].  The corrector MLP simply runs over the halo
+rows too (zero input features, result overwritten by the exchange), so every kernel of the single-GPU
+engine is reused unchanged on rank-local CSR blocks whose columns index that row space.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .engine import TrainStepEngine, FlatParams, StepConfig
+from .partition import LevelPlan
+from .sparse import OperatorPair
+
+
+class HaloExchanger:
+    """Moves the rows listed in plan.send to their peers and receives this rank's halo block.
+    gather(src_rows_tensor, idx_tensor) -> packed rows; injected so the host logic can be exercised on
+    CPU tensors (gloo) in the tests while the product passes the CUDA gather kernel."""
+
+    def __init__(self, plan: LevelPlan, device, gather, group=None):
+        self.plan, self.group, self.gather = plan, group, gather
+        self.send_idx = {p: torch.from_numpy(ix).to(device) for p, ix in sorted(plan.send.items())}
+        self.recv = dict(sorted(plan.recv.items()))
+
+    def exchange(self, rows, n_own):
+        """rows: (n_own + n_halo) x k tensor; fills rows[n_own:] from the owners."""
+        reqs, keep = [], []
+        for p, idx in self.send_idx.items():
+            buf = self.gather(rows, idx)
+            keep.append(buf)
+            reqs.append(dist.P2POp(dist.isend, buf, p, self.group))
+        for p, (off, cnt) in self.recv.items():
+            reqs.append(dist.P2POp(dist.irecv, rows[n_own + off:n_own + off + cnt], p, self.group))
+        if reqs:
+            for w in dist.batch_isend_irecv(reqs):
+                w.wait()
+        return rows
+
+
+def resolve_send_lists(plan: LevelPlan, group=None):
+    """Every rank tells every other rank which of its rows it needs (one all_gather of small index lists)."""
+    world = dist.get_world_size(group)
+    mine = {p: ids.tolist() for p, ids in plan.requests().items()}
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine, group=group)
+    wanted = {p: np.asarray(everyone[p].get(plan.rank, []), dtype=np.int64) for p in range(world) if p != plan.rank}
+    plan.set_send_lists(wanted)
+    return plan
+
+
+class ShardedTrainStepEngine(TrainStepEngine):
+    def __init__(self, h_local, U_base_local, plans, params: FlatParams, cfg: StepConfig, lam_target=None,
+                 mlp_mode="fp32", group=None, symmetric=True):
+        dev = h_local.device
+        self.plans, self.group = plans, group
+        pairs = [OperatorPair(pl.K_local, pl.M_local, dev, assume_symmetric=symmetric) for pl in plans]
+        for pair, pl in zip(pairs, plans):
+            pair.n = pl.n_own
+        offsets, off = [], 0
+        for pl in plans:
+            offsets.append(off)
+            off += pl.n_own + pl.n_halo
+        assert off == h_local.shape[0] == U_base_local.shape[0]
+        super().__init__(h_local, U_base_local, pairs, offsets, params, cfg, lam_target, mlp_mode)
+        self.halo = [HaloExchanger(pl, dev, lambda rows, idx: ops.gather_rows(rows, idx), group) for pl in plans]
+        self.dCorr.zero_()                      # halo rows never receive a gradient on this rank
+
+    def _ext(self, buf, li):
+        pl = self.plans[li]
+        off = self.offsets[li]
+        return buf[off:off + pl.n_own + pl.n_halo]
+
+    def _n_global(self, li):
+        return self.plans[li].n_global
+
+    def _reduce_partials(self, li):
+        dist.all_reduce(self.partials[li], group=self.group)
+
+    def _reduce_grads(self):
+        dist.all_reduce(self.params.grad, group=self.group)
+
+    def loss_forward(self):
+        for li, pl in enumerate(self.plans):
+            self.halo[li].exchange(self._ext(self.U_pred, li), pl.n_own)
+        super().loss_forward()
+
+    def loss_backward(self, scale):
+        for li, pl in enumerate(self.plans):
+            self.halo[li].exchange(self._ext(self.KU, li), pl.n_own)
+            self.halo[li].exchange(self._ext(self.MU, li), pl.n_own)
+        super().loss_backward(scale)
+
+
+def shard_rows(global_rows, plans, global_offsets):
+    """Stack [owned | zero halo] blocks of every level from a stacked global array."""
+    blocks = []
+    for pl, goff in zip(plans, global_offsets):
+        blocks.append(global_rows[goff + pl.lo:goff + pl.hi])
+        blocks.append(torch.zeros((pl.n_halo, global_rows.shape[1]), dtype=global_rows.dtype, device=global_rows.device))
+    return torch.cat(blocks, dim=0).contiguous()
+
+
+def make_sharded_engine(gnn, x_feats, edge_index, U_base, K, M, lam_target, optimizer, rank, world, group=None):
+    """Single-level helper used by bench.py: every rank holds the global arrays once at set-up, keeps its
+    vertex range, and builds the rank-local engine."""
+    import torch.nn as nn
+    dev = gnn.device
+    h_global = gnn.model.corrector_input(x_feats.to(dev), edge_index.to(dev))
+    plan = resolve_send_lists(LevelPlan(K, M, rank, world), group)
+    h_local = shard_rows(h_global, [plan], [0])
+    U_local = shard_rows(U_base.to(dev), [plan], [0])
+    del h_global
+    linears = [m for m in gnn.model.net if isinstance(m, nn.Linear)]
+    params = FlatParams.adopt(linears)
+    g = optimizer.param_groups[0]
+    cfg = StepConfig(lr=g['lr'], weight_decay=g['weight_decay'], corr_scale=gnn.corr_scale, w_res=gnn.w_res,
+                     w_orth=gnn.w_orth, w_trace=gnn.w_trace, w_order=gnn.w_order, w_eigen=gnn.w_eigen,
+                     grad_clip=gnn.grad_clip, beta1=g['betas'][0], beta2=g['betas'][1], eps=g['eps'])
+    return ShardedTrainStepEngine(h_local, U_local, [plan], params, cfg, lam_target=lam_target,
+                                  mlp_mode=gnn.mlp_mode, group=group)

@@ -95,7 +95,9 @@ class OperatorPair:
     (always true for the FEM operators of src/Mesh.py) the dual kernel reads each gathered
     row of U once for both products."""
 
-    def __init__(self, K, M, device):
+    def __init__(self, K, M, device, assume_symmetric=None):
+        """assume_symmetric=True: the GLOBAL operators are symmetric although these (possibly rectangular,
+        rank-local [owned | halo] column space) blocks cannot be checked - skips the transposes."""
         self.K = K if isinstance(K, CsrMatrix) else CsrMatrix.from_scipy(K, device)
         self.M = M if isinstance(M, CsrMatrix) else CsrMatrix.from_scipy(M, device)
         assert self.K.shape == self.M.shape
@@ -104,7 +106,7 @@ class OperatorPair:
                        and torch.equal(self.K.col, self.M.col))
         if not self.shared:
             self._unify()
-        self.symmetric = self.K.symmetric and self.M.symmetric
+        self.symmetric = bool(assume_symmetric) if assume_symmetric is not None else (self.K.symmetric and self.M.symmetric)
         if self.symmetric:
             self.KT, self.MT = self.K, self.M
         else:
