@@ -1,0 +1,63 @@
+"""torchrun entry: the vertex-sharded engine on WORLD_SIZE GPUs must reproduce the single-GPU engine
+(same losses step by step, same weights afterwards).  Launched by tests/test_gpu_multi.py."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "eigen-pinns_b200", "src"))
+
+
+def main():
+    mode = sys.argv[1] if len(sys.argv) > 1 else "fp32"
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    import bench
+    import config as cfg_mod
+    import multigrid_model
+    de = importlib.import_module("eigen-pinns_b200.dist_engine")
+    w = bench.build_host_workload("icosphere10k")
+    k = w["k"]
+    cfg = cfg_mod.PINNConfig.from_yaml(os.path.join(ROOT, "eigen-pinns_b200", "src", "parameters.yml"))
+    cfg.n_modes, cfg.mlp_mode, cfg.seed, cfg.hidden_layers = k, mode, 0, [256, 256]
+    sys.stdout = open(os.devnull, "w")
+    results = []
+    for sharded in (False, True):
+        gnn = multigrid_model.MultigridGNN(cfg)
+        edges = torch.from_numpy(w["edges"])
+        U_norm = gnn._normalize_eigenvectors([w["U0"]], [w["M"]])
+        lam0 = torch.linspace(0, 1, k)
+        x_feats, edge_all, A_norm = gnn._build_features([w["verts"]], U_norm, [lam0], [edges], [w["K"]], [w["M"]])
+        gnn._initialize_model(x_feats.shape[1], k, cfg.hidden_layers, 0.0)
+        opt, _ = gnn._create_optimizer(gnn.lr, gnn.weight_decay)
+        if sharded:
+            eng = de.make_sharded_engine(gnn, x_feats, edge_all, U_norm[0], w["K"], w["M"], lam0, opt, rank, world)
+        else:
+            eng = gnn._make_engine(x_feats, edge_all, A_norm, U_norm[0], [w["K"]], [w["M"]], lam0, [0], opt)
+        losses = [eng.step(2500 + i).cpu().numpy().copy() for i in range(4)]
+        results.append((np.array(losses), eng.params.flat.clone(), [l.clone() for l in eng.lams]))
+    sys.stdout = sys.__stdout__
+    (l1, p1, lam1), (l2, p2, lam2) = results
+    tol = 1e-5 if mode == "fp32" else 2e-3
+    ok = np.allclose(l1, l2, rtol=tol, atol=1e-9)
+    perr = (p1 - p2).abs().max().item()
+    ok = ok and perr <= (2e-5 if mode == "fp32" else 2e-3)
+    ok = ok and torch.allclose(lam1[0], lam2[0], rtol=tol, atol=1e-6)
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("MULTI_GPU_CHECK", "OK" if flag.item() == 1.0 else "FAIL", "world", world, "mode", mode,
+              "loss_single", l1[:, 5].tolist(), "loss_sharded", l2[:, 5].tolist(), "param_err", perr)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()
