@@ -315,7 +315,7 @@ def run_ours(args):
                  "peak": peaks["hbm"], "unit": "GB/s", "frac": spmm_gbs / peaks["hbm"], "ms": spmm_ms,
                  "bytes_per_launch": spmm_bytes, "traffic": None}
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         kind, size, _ = WORKLOADS[args.workload]
         sample = "icosphere100k" if kind == "icosphere" else "torus1m"
         if n_global < 150000:
