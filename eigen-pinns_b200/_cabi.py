@@ -46,9 +46,9 @@ SIGNATURES = {
     "ep_tc_linear_fwd_bf16": (c_int, [c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_int, c_p, c_p, c_p]),
     "ep_tc_linear_final_bf16": (c_int, [c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_int, c_p, c_f, c_p,
                                         c_p, c_int, c_p]),
-    "ep_tc_linear_dx_bf16": (c_int, [c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_p]),
+    "ep_tc_linear_dx_bf16": (c_int, [c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_int, c_p]),
     "ep_tc_dw_workspace_bytes": (c_sz, []),
-    "ep_tc_linear_dw_bf16": (c_int, [c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "ep_tc_linear_dw_bf16": (c_int, [c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_sz, c_int, c_p]),
     "ep_grad_sqnorm_f32": (c_int, [c_sz, c_p, c_p, c_p]),
     "ep_adam_clip_step_f32": (c_int, [c_sz, c_p, c_p, c_p, c_p, c_f, c_p, c_f, c_f, c_f, c_f, c_int, c_f,
                                       c_p, c_p]),

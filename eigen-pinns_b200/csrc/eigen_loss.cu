@@ -10,6 +10,7 @@
 namespace {
 
 constexpr int kPartialThreads = 256;
+__device__ __forceinline__ bool ep_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 __host__ __device__ inline int partials_len(int k) { return k * k + 4 * k; }
 
@@ -58,18 +59,55 @@ eigen_partials_kernel(int n, int k, const float* __restrict__ U, int ldu, const 
 
   const int n_tiles = (n + R - 1) / R;
   int since_flush = 0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  // Register-staged double buffering: the next tile's global loads are in flight while this tile is reduced.
+  constexpr int VPT = (R * KP / 4 + kPartialThreads - 1) / kPartialThreads;     // float4 per thread per array
+  const bool vec_ok = (k % 4 == 0) && (ldu % 4 == 0) && (ld % 4 == 0) && ep_aligned16(U) && ep_aligned16(KU) && ep_aligned16(MU);
+  float4 pu[VPT], pk[VPT], pm[VPT];
+  auto prefetch = [&](int tile) {
     const int row0 = tile * R;
-    __syncthreads();
-    for (int e = tid; e < R * KP; e += kPartialThreads) {
-      const int r = e / KP, c = e - r * KP;
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      const int e4 = tid + v * kPartialThreads;          // float4 index inside the R x KP tile
+      const int r = e4 / (KP / 4), c = (e4 - r * (KP / 4)) * 4;
       const int row = row0 + r;
-      const bool ok = (row < n) && (c < k);
-      Us[r][c] = ok ? __ldg(U + (size_t)row * ldu + c) : 0.f;
-      KUs[r][c] = ok ? __ldg(KU + (size_t)row * ld + c) : 0.f;
-      MUs[r][c] = ok ? __ldg(MU + (size_t)row * ld + c) : 0.f;
+      float4 zu = make_float4(0.f, 0.f, 0.f, 0.f), zk = zu, zm = zu;
+      if (r < R && row < n && c < k) {
+        if (vec_ok) {
+          zu = __ldg(reinterpret_cast<const float4*>(U + (size_t)row * ldu + c));
+          zk = __ldg(reinterpret_cast<const float4*>(KU + (size_t)row * ld + c));
+          zm = __ldg(reinterpret_cast<const float4*>(MU + (size_t)row * ld + c));
+        } else {
+          float tu[4], tk[4], tm[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const bool ok = (c + j) < k;
+            tu[j] = ok ? __ldg(U + (size_t)row * ldu + c + j) : 0.f;
+            tk[j] = ok ? __ldg(KU + (size_t)row * ld + c + j) : 0.f;
+            tm[j] = ok ? __ldg(MU + (size_t)row * ld + c + j) : 0.f;
+          }
+          zu = make_float4(tu[0], tu[1], tu[2], tu[3]);
+          zk = make_float4(tk[0], tk[1], tk[2], tk[3]);
+          zm = make_float4(tm[0], tm[1], tm[2], tm[3]);
+        }
+      }
+      pu[v] = zu; pk[v] = zk; pm[v] = zm;
+    }
+  };
+  if ((int)blockIdx.x < n_tiles) prefetch(blockIdx.x);
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    __syncthreads();
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      const int e4 = tid + v * kPartialThreads;
+      const int r = e4 / (KP / 4), c = (e4 - r * (KP / 4)) * 4;
+      if (r < R) {
+        *reinterpret_cast<float4*>(&Us[r][c]) = pu[v];
+        *reinterpret_cast<float4*>(&KUs[r][c]) = pk[v];
+        *reinterpret_cast<float4*>(&MUs[r][c]) = pm[v];
+      }
     }
     __syncthreads();
+    if (tile + (int)gridDim.x < n_tiles) prefetch(tile + gridDim.x);
 #pragma unroll 2
     for (int r = sg; r < R; r += NSG) {
       float a[TG], b[TG];
@@ -159,24 +197,16 @@ eigen_partials_kernel(int n, int k, const float* __restrict__ U, int ldu, const 
   }
 }
 
-// sum of the per-block partials: 64 outputs per block, 4 thread groups over the blocks, fixed order
+// sum of the per-block partials: one warp per output, lanes stride over the blocks, fixed shuffle tree
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(int n_blocks, int len, const double* __restrict__ block_out, double* __restrict__ out) {
-  __shared__ double sh[4][64];
-  const int el = threadIdx.x & 63, g = threadIdx.x >> 6;
-  const int e = blockIdx.x * 64 + el;
-  double s0 = 0.0, s1 = 0.0;
-  if (e < len) {
-    int b = g;
-    for (; b + 4 < n_blocks; b += 8) {
-      s0 += block_out[(size_t)b * len + e];
-      s1 += block_out[(size_t)(b + 4) * len + e];
-    }
-    for (; b < n_blocks; b += 4) s0 += block_out[(size_t)b * len + e];
-  }
-  sh[g][el] = s0 + s1;
-  __syncthreads();
-  if (g == 0 && e < len) out[e] = (sh[0][el] + sh[1][el]) + (sh[2][el] + sh[3][el]);
+  const int e = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (e >= len) return;
+  double s = 0.0;
+  for (int b = lane; b < n_blocks; b += 32) s += block_out[(size_t)b * len + e];
+  s = ep::warp_sum(s);
+  if (lane == 0) out[e] = s;
 }
 
 __device__ double block_sum_256(double v, double* scratch) {
@@ -373,6 +403,7 @@ eigen_bwd_prepare_kernel(int n, int k, const float* __restrict__ U, int ldu, con
 // writes dU once -> 12 nnz + 4 (n+1) + 12 n k bytes, like the forward dual SpMM.
 // Thread layout as in the SpMM: LPR lanes per row, 4 columns per lane; the k x k product takes the row's
 // MU values from the other lanes with shuffles and S from shared memory.
+template <int KVT>     // KVT = k / 4 when instantiated for a fixed width (fully unrolled product), 0 = generic
 __global__ void __launch_bounds__(256)
 eigen_bwd_fused_sym_kernel(int n, int k, int lpr_shift, const int32_t* __restrict__ rowptr,
                            const int32_t* __restrict__ col, const float* __restrict__ valK,
@@ -398,7 +429,7 @@ eigen_bwd_fused_sym_kernel(int n, int k, int lpr_shift, const int32_t* __restric
   __syncthreads();
 
   const int lpr = 1 << lpr_shift;
-  const int kv = k >> 2;
+  const int kv = KVT > 0 ? KVT : (k >> 2);
   const int lane_r = threadIdx.x & (lpr - 1);
   const bool active = lane_r < kv;
   const int cofs = active ? 4 * lane_r : 0;
@@ -447,6 +478,7 @@ eigen_bwd_fused_sym_kernel(int n, int k, int lpr_shift, const int32_t* __restric
       acc.z = fmaf(a24.z, ku_i.z, acc.z); acc.w = fmaf(a24.w, ku_i.w, acc.w);
     }
     // acc += MU_i S : lane L of the row group holds MU_i[4L .. 4L+3]
+#pragma unroll
     for (int L = 0; L < kv; ++L) {
       const float m0 = __shfl_sync(0xffffffffu, mu_i.x, L, lpr);
       const float m1 = __shfl_sync(0xffffffffu, mu_i.y, L, lpr);
@@ -548,7 +580,7 @@ int ep_eigen_partials_f32(int n, int k, const float* U, int ldu, const float* KU
   else if (k <= 64) eigen_partials_kernel<64, 4><<<grid, kPartialThreads, 0, st>>>(n, k, U, ldu, KU, MU, ld, blocks);
   else              eigen_partials_kernel<128, 8><<<grid, kPartialThreads, 0, st>>>(n, k, U, ldu, KU, MU, ld, blocks);
   EP_LAUNCH_CHECK("eigen_partials_kernel");
-  reduce_partials_kernel<<<ep::ceil_div(len, 64), 256, 0, st>>>(grid, len, blocks, out);
+  reduce_partials_kernel<<<ep::ceil_div(len, 8), 256, 0, st>>>(grid, len, blocks, out);
   EP_LAUNCH_CHECK("reduce_partials_kernel");
   return EP_OK;
 }
@@ -597,15 +629,25 @@ int ep_eigen_bwd_fused_sym_f32(int n, int k, const int32_t* rowptr, const int32_
   const size_t smem = sizeof(float) * ((size_t)k * k + 2 * k);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    EP_CUDA_CHECK(cudaFuncSetAttribute(eigen_bwd_fused_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EP_CUDA_CHECK(cudaFuncSetAttribute(eigen_bwd_fused_sym_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EP_CUDA_CHECK(cudaFuncSetAttribute(eigen_bwd_fused_sym_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   const long long threads = (long long)n << lpr_shift;
   long long grid = (threads + 255) / 256;
   const long long cap = (long long)ep::sm_count() * 8;
   if (grid > cap) grid = cap;
-  eigen_bwd_fused_sym_kernel<<<(unsigned)grid, 256, smem, ep::as_stream(stream)>>>(
-      n, k, lpr_shift, rowptr, col, valK, valM, KU, MU, ld, coef, out_scale, dU, ldo);
+  cudaStream_t st = ep::as_stream(stream);
+#define EP_FUSED_LAUNCH(KVT) eigen_bwd_fused_sym_kernel<KVT><<<(unsigned)grid, 256, smem, st>>>( \
+      n, k, lpr_shift, rowptr, col, valK, valM, KU, MU, ld, coef, out_scale, dU, ldo)
+  switch (kv) {
+    case 4: EP_FUSED_LAUNCH(4); break;
+    case 8: EP_FUSED_LAUNCH(8); break;
+    case 16: EP_FUSED_LAUNCH(16); break;
+    case 32: EP_FUSED_LAUNCH(32); break;
+    default: EP_FUSED_LAUNCH(0); break;
+  }
+#undef EP_FUSED_LAUNCH
   EP_LAUNCH_CHECK("eigen_bwd_fused_sym_kernel");
   return EP_OK;
 }

@@ -588,7 +588,7 @@ using namespace tc;
 namespace {
 
 template <int MODE>
-int launch_linear(const LinearArgs& a, cudaStream_t st) {
+int launch_linear(const LinearArgs& a, cudaStream_t st, int max_ctas = 0) {
   const size_t smem = (size_t)a.KC * a.N * 16 + (size_t)N_STAGES * STAGE_BYTES + 8 * (2 * N_STAGES + 5) + 16 +
                       sizeof(float) * a.N + (MODE == MODE_FINAL ? sizeof(float) * 4 * 32 * 33 : 0) + 128;
   static size_t configured = 0;
@@ -597,6 +597,7 @@ int launch_linear(const LinearArgs& a, cudaStream_t st) {
     configured = smem;
   }
   int grid = ep::sm_count();
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if (grid > a.n_tiles) grid = a.n_tiles;
   tc_linear_kernel<MODE><<<grid, LINEAR_THREADS, smem, st>>>(a);
   EP_LAUNCH_CHECK("tc_linear_kernel");
@@ -673,7 +674,7 @@ int ep_tc_linear_final_bf16(int n, int in_padded, int out, int out_padded, const
 }
 
 int ep_tc_linear_dx_bf16(int n, int out_padded, int in_padded, const void* dZ_packed, const void* WTp,
-                         const void* relu_mask, void* dZprev_packed, ep_stream_t stream) {
+                         const void* relu_mask, void* dZprev_packed, int max_ctas, ep_stream_t stream) {
   EP_REQUIRE(n > 0 && dZ_packed && WTp && relu_mask && dZprev_packed, "bad argument");
   if (!dims_ok(out_padded, in_padded)) { ep::set_error("ep_tc_linear_dx_bf16: unsupported dims"); return EP_ERR_UNSUPPORTED; }
   LinearArgs a{};
@@ -681,14 +682,14 @@ int ep_tc_linear_dx_bf16(int n, int out_padded, int in_padded, const void* dZ_pa
   a.n_tiles = n_tiles_for(n); a.KC = out_padded / 8; a.N = in_padded;
   a.out_packed = static_cast<uint8_t*>(dZprev_packed); a.mask_in = static_cast<const uint32_t*>(relu_mask);
   a.n_rows = n; a.n_out = in_padded;
-  return launch_linear<MODE_DX>(a, ep::as_stream(stream));
+  return launch_linear<MODE_DX>(a, ep::as_stream(stream), max_ctas);
 }
 
 size_t ep_tc_dw_workspace_bytes(void) { return sizeof(float) * (size_t)ep::sm_count() * (256 * 256 + 256); }
 
 int ep_tc_linear_dw_bf16(int n, int out, int in, int out_padded, int in_padded, const void* dZ_packed,
                          const void* act_packed, float* dW, float* db, void* workspace, size_t workspace_bytes,
-                         ep_stream_t stream) {
+                         int max_ctas, ep_stream_t stream) {
   EP_REQUIRE(n > 0 && dZ_packed && act_packed && dW && db && workspace, "bad argument");
   EP_REQUIRE(out <= out_padded && in <= in_padded, "bad padding");
   if (workspace_bytes < ep_tc_dw_workspace_bytes()) { ep::set_error("ep_tc_linear_dw_bf16: workspace too small"); return EP_ERR_WORKSPACE; }
@@ -706,6 +707,7 @@ int ep_tc_linear_dw_bf16(int n, int out, int in, int out_padded, int in_padded, 
   }
   a.n_tiles = n_tiles_for(n);
   int grid = ep::sm_count();
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if (grid > a.n_tiles) grid = a.n_tiles;
   a.partial = static_cast<float*>(workspace);
   a.db_partial = a.partial + (size_t)ep::sm_count() * 256 * 256;

@@ -58,6 +58,9 @@ class TcMlp:
         self.ws_bytes = query("ep_tc_dw_workspace_bytes")
         self.ws = torch.empty(self.ws_bytes, **u8)
         self.corr = torch.empty((n, dims[-1]), dtype=torch.float32, device=device)
+        self.side_stream = torch.cuda.Stream(device=device)
+        self.sm_count = torch.cuda.get_device_properties(device).multi_processor_count
+        self.overlap = True
         self._packed_version = None
         if h is not None:
             self.input_changed(h)
@@ -88,15 +91,30 @@ class TcMlp:
         return self.corr
 
     def backward(self, h, d_out):
+        """dW / db of every layer into the flat gradient buffer.  For each layer the dW kernel (side stream) and
+        the dX kernel (main stream) run concurrently on half of the SMs each, walking the tiles in the same order:
+        the dZ tile that one of them pulls from HBM is an L2 hit for the other, so dZ is read from DRAM once."""
         L = self.L
+        main = torch.cuda.current_stream()
+        side = self.side_stream
         pack_rows(d_out, self.pd[-1], out=self.dz_out)
         dz, dz_w = self.dz_out, self.pd[-1]
+        half = max(1, self.sm_count // 2)
         for l in range(L - 1, -1, -1):
             act = self.acts[l - 1] if l > 0 else self.x0
-            call("ep_tc_linear_dw_bf16", self.n, self.dims[l + 1], self.dims[l], dz_w, self.pd[l], _p(dz), _p(act),
-                 _p(self.p.dW[l]), _p(self.p.db[l]), _p(self.ws), self.ws_bytes, _stream())
+            concurrent = self.overlap and l > 0
+            if concurrent:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    call("ep_tc_linear_dw_bf16", self.n, self.dims[l + 1], self.dims[l], dz_w, self.pd[l], _p(dz), _p(act),
+                         _p(self.p.dW[l]), _p(self.p.db[l]), _p(self.ws), self.ws_bytes, half, _stream())
+            else:
+                call("ep_tc_linear_dw_bf16", self.n, self.dims[l + 1], self.dims[l], dz_w, self.pd[l], _p(dz), _p(act),
+                     _p(self.p.dW[l]), _p(self.p.db[l]), _p(self.ws), self.ws_bytes, 0, _stream())
             if l > 0:
                 nxt = self.dz[l & 1]
                 call("ep_tc_linear_dx_bf16", self.n, dz_w, self.pd[l], _p(dz), _p(self.WTp[l]), _p(self.masks[l - 1]),
-                     _p(nxt), _stream())
+                     _p(nxt), half if concurrent else 0, _stream())
+                if concurrent:
+                    main.wait_stream(side)
                 dz, dz_w = nxt, self.pd[l]

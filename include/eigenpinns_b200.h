@@ -191,14 +191,16 @@ EP_API int ep_tc_linear_fwd_bf16(int n, int in_padded, int out, int out_padded, 
 EP_API int ep_tc_linear_final_bf16(int n, int in_padded, int out, int out_padded, const void* A_packed, const void* Wp,
                             const float* bias, float* corr, int ldc, const float* U_base, float scale,
                             const float* scale_dev, float* U_pred, int ldu, ep_stream_t stream);
-/* dZ_prev = (dZ W) * [act > 0]; the ReLU mask of the previous layer is the bit mask its forward wrote. */
+/* dZ_prev = (dZ W) * [act > 0]; the ReLU mask of the previous layer is the bit mask its forward wrote.
+ * max_ctas > 0 limits the persistent grid (dX and dW of one layer run concurrently on two streams, half the
+ * SMs each and the same tile order, so the dZ tiles one of them pulls from HBM are L2 hits for the other). */
 EP_API int ep_tc_linear_dx_bf16(int n, int out_padded, int in_padded, const void* dZ_packed, const void* WTp,
-                         const void* relu_mask, void* dZprev_packed, ep_stream_t stream);
+                         const void* relu_mask, void* dZprev_packed, int max_ctas, ep_stream_t stream);
 /* dW = dZ^T act (fp32 [out x in]) and db = column sums of dZ; deterministic two-stage reduction. */
 EP_API size_t ep_tc_dw_workspace_bytes(void);
 EP_API int ep_tc_linear_dw_bf16(int n, int out, int in, int out_padded, int in_padded, const void* dZ_packed,
                          const void* act_packed, float* dW, float* db, void* workspace, size_t workspace_bytes,
-                         ep_stream_t stream);
+                         int max_ctas, ep_stream_t stream);
 
 /* ---- optimiser: clip_grad_norm_ + Adam(weight_decay) step, multigrid_model.py:218-220,259-260
  * Parameters / gradients / moments live in one flat fp32 buffer each.
