@@ -34,6 +34,9 @@ WORKLOADS = {
     "torus1m": ("torus", 1024, 64),
 }
 HIDDEN = [256] * 6                               # reference default (src/parameters.yml)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch / vertices of tc_linear_kernel<HIDDEN> from the committed
+# ncu --set full capture (profiles/r01_v1_ncu_full_summary.csv: 0.5115 GB + 0.459 GB at 998,562 vertices)
+NCU_TRAFFIC_HIDDEN_PER_VERTEX = (0.5115e9 + 0.459e9) / 998562
 
 
 def pkg(name=None):
@@ -281,22 +284,63 @@ def run_ours(args):
     n_loc = pair.n
     spmm_bytes = 12 * pair.K.nnz + 4 * (n_loc + 1) + 12 * n_loc * k
     peaks = measured_peaks()
+    # ---- dominant kernel alone: one hidden layer of the tensor-core MLP (same kernel serves forward and dX)
+    hidden_ms, hidden_bytes = None, 0
+    if args.mlp_mode == "bf16":
+        import ctypes
+        m = eng.mlp
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        run = lambda: cabi.call("ep_tc_linear_fwd_bf16", m.n, m.pd[1], m.dims[2], m.pd[2], P(m.acts[0]), P(m.Wp[1]),
+                                P(m.p.b[1]), 1, P(m.acts[1]), P(m.masks[1]), st())
+        run()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        hidden_ms = e0.elapsed_time(e1) / reps
+        n_pad = (m.n + 127) // 128 * 128
+        hidden_bytes = n_pad * (m.pd[1] + m.pd[2]) * 2 + n_pad * (m.pd[2] // 8)
 
-    # ---- end to end: inputs in pinned host memory every step, loss read back every step
+    # ---- host issue time (how long Python + ctypes take to enqueue one step)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(5):
+        eng.step(epoch0 + i)
+    host_issue_ms = (time.perf_counter() - t0) / 5 * 1e3
+    torch.cuda.synchronize()
+
+    # ---- end to end through the public host-fed API: every step uploads its inputs (node features x and the base
+    # subspace U_base) from pinned host memory and returns the loss to the host
     e2e = None
     if world == 1 and not args.no_e2e:
-        h_host = eng.h.cpu().pin_memory()
-        ub_host = eng.U_base.cpu().pin_memory()
-        for i in range(2):
-            eng.step_from_host(h_host, ub_host, epoch0 + i)
+        engine_mod = pkg("engine")
+        sparse = pkg("sparse")
+        adj = sparse.CsrMatrix.from_edge_index(edge_all, n, dev)
+        pipe = engine_mod.HostFedPipeline(eng, lambda x, out: ops.neighbor_mean_concat(x, adj, out=out))
+        x_host = x_feats.detach().cpu().pin_memory()
+        ub_host = U_norm[0].detach().cpu().pin_memory()
+        prev = pipe.submit(x_host, ub_host, epoch0)
+        for i in range(1, 3):
+            cur = pipe.submit(x_host, ub_host, epoch0 + i)
+            pipe.result(prev)
+            prev = cur
+        pipe.result(prev)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for i in range(args.steps):
-            eng.step_from_host(h_host, ub_host, epoch0 + i)
-        torch.cuda.synchronize()
+        prev = pipe.submit(x_host, ub_host, epoch0)
+        e2e_loss = None
+        for i in range(1, args.steps + 1):
+            cur = pipe.submit(x_host, ub_host, epoch0 + i) if i < args.steps else None
+            e2e_loss = pipe.result(prev)
+            prev = cur
         dt = (time.perf_counter() - t0) / args.steps
-        e2e = {"value": 1.0 / dt, "unit": "steps/s", "h2d_bytes_per_step": int(h_host.numel() * 4 + ub_host.numel() * 4),
-               "d2h_bytes_per_step": 48}
+        e2e = {"value": 1.0 / dt, "unit": "steps/s", "h2d_bytes_per_step": int(pipe.h2d_bytes),
+               "d2h_bytes_per_step": int(pipe.d2h_bytes), "ms_per_step": dt * 1e3,
+               "api": "engine.HostFedPipeline.submit/result (x_feats + U_base uploaded every step, loss read back)",
+               "loss": float(e2e_loss[5])}
 
     if rank != 0:
         if world > 1:
@@ -306,10 +350,20 @@ def run_ours(args):
     n_global = n
     tflops = flops_v * n_global / world / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
     tensor_peak = peaks["bf16_sustained"]
-    roofline = {"bound": "tensor", "kernel": "corrector MLP forward+backward (%s)" % args.mlp_mode, "achieved": tflops,
-                "peak": tensor_peak, "unit": "TFLOP/s", "frac": tflops / tensor_peak, "traffic": None,
-                "peak_source": peaks["source"] + " bf16 sustained", "ms_per_step": mlp_ms,
-                "flop_per_vertex": flops_v}
+    mlp_roof = {"bound": "tensor", "kernel": "corrector MLP forward+backward, all layers (%s)" % args.mlp_mode,
+                "achieved": tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tflops / tensor_peak,
+                "peak_source": peaks["source"] + " bf16 sustained", "ms_per_step": mlp_ms, "flop_per_vertex": flops_v,
+                "note": "each layer kernel is HBM-bound (AI 128 flop/B < ridge); see roofline for the dominant kernel"}
+    if hidden_ms is not None:
+        gbs = hidden_bytes / (hidden_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "tc_linear_kernel<HIDDEN> (tcgen05, one 256->256 layer: relu(A W^T + b) -> packed bf16 + mask)",
+                    "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                    "traffic": NCU_TRAFFIC_HIDDEN_PER_VERTEX * n_loc if n_loc else None,
+                    "peak_source": peaks["source"] + " hbm copy", "ms": hidden_ms, "bytes_per_launch": hidden_bytes,
+                    "launches_per_step": 12, "share_of_step": 12 * hidden_ms / ms_step,
+                    "tflops_this_kernel": 2.0 * n_loc * 256 * 256 / (hidden_ms * 1e-3) / 1e12}
+    else:
+        roofline = dict(mlp_roof, traffic=None)
     spmm_gbs = spmm_bytes / (spmm_ms * 1e-3) / 1e9
     spmm_roof = {"bound": "hbm", "kernel": "ep_spmm2_csr_f32 (K U and M U, shared pattern)", "achieved": spmm_gbs,
                  "peak": peaks["hbm"], "unit": "GB/s", "frac": spmm_gbs / peaks["hbm"], "ms": spmm_ms,
@@ -332,9 +386,9 @@ def run_ours(args):
                        "nnz_per_operator": int(nnz), "mlp_mode": args.mlp_mode, "levels": 1,
                        "parallelism": "vertex-shard x%d" % world,
                        "l2": "inputs larger than L2 (U, KU, MU, activations >> 126 MB)"},
-            "clocks": clk, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,
+            "clocks": clk, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "mlp_roofline": mlp_roof,
             "spmm_roofline": spmm_roof, "cpu_baseline": cpu,
-            "phase_ms": phase, "loss": loss_now, "lambda_rel_err_rayleigh_ritz": lam_err}
+            "phase_ms": phase, "host_issue_ms": host_issue_ms, "loss": loss_now, "lambda_rel_err_rayleigh_ritz": lam_err}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

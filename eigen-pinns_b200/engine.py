@@ -209,10 +209,62 @@ class TrainStepEngine:
         return self.loss_acc
 
     def step_from_host(self, h_host, U_base_host, epoch, lr=None):
-        """End-to-end variant: this step's inputs arrive in (pinned) host memory, the loss goes back to the
-        host.  Returns the six loss terms as a numpy array (one synchronising D2H copy)."""
+        """Simplest end-to-end variant: this step's corrector input and base subspace arrive in (pinned) host
+        memory, the loss goes back to the host (one synchronising D2H copy)."""
         self.h.copy_(h_host, non_blocking=True)
         self.U_base.copy_(U_base_host, non_blocking=True)
         if hasattr(self.mlp, "input_changed"):
             self.mlp.input_changed(self.h)
         return self.step(epoch, lr).cpu().numpy()
+
+
+class HostFedPipeline:
+    """End-to-end driver with HOST inputs every step: node features x (n x d) and the base subspace U_base
+    (n x k) live in pinned host memory.  Uploads go through a copy stream into one of two staging sets, so the
+    upload of step i+1 overlaps the kernels of step i; the aggregation [x | mean_nbr x] and (bf16 mode) the
+    packing run on the device; the six loss terms return through a pinned 48-byte buffer.
+
+        handle = pipe.submit(x_host, U_host, epoch, lr)      # asynchronous
+        losses = pipe.result(handle)                         # waits for that step only
+    """
+
+    def __init__(self, engine, aggregate):
+        """aggregate(x_dev, out) fills out = corrector input h from the uploaded features."""
+        self.e, self.aggregate = engine, aggregate
+        dev = engine.dev
+        n, d2 = engine.h.shape
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.x_dev = [torch.empty((n, d2 // 2), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.u_dev = [torch.empty_like(engine.U_base) for _ in range(2)]
+        self.uploaded = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.loss_host = [torch.empty(6, dtype=torch.float64).pin_memory() for _ in range(2)]
+        self.done = [torch.cuda.Event() for _ in range(2)]
+        self.count = 0
+        self.h2d_bytes = self.x_dev[0].numel() * 4 + self.u_dev[0].numel() * 4
+        self.d2h_bytes = 48
+
+    def submit(self, x_host, U_host, epoch, lr=None):
+        s = self.count & 1
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self.copy_stream):
+            if self.count >= 2:
+                self.copy_stream.wait_event(self.consumed[s])
+            self.x_dev[s].copy_(x_host, non_blocking=True)
+            self.u_dev[s].copy_(U_host, non_blocking=True)
+            self.uploaded[s].record(self.copy_stream)
+        main.wait_event(self.uploaded[s])
+        self.aggregate(self.x_dev[s], self.e.h)
+        if hasattr(self.e.mlp, "input_changed"):
+            self.e.mlp.input_changed(self.e.h)
+        self.e.U_base = self.u_dev[s]
+        acc = self.e.step(epoch, lr)
+        self.consumed[s].record(main)
+        self.loss_host[s].copy_(acc, non_blocking=True)
+        self.done[s].record(main)
+        self.count += 1
+        return s
+
+    def result(self, handle):
+        self.done[handle].synchronize()
+        return self.loss_host[handle].numpy().copy()

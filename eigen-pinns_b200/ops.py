@@ -88,21 +88,21 @@ def spmm_autograd(A, X):
 
 
 # ------------------------------------------------------------------------------- aggregation
-def neighbor_mean_concat(x, adj: CsrMatrix):
+def neighbor_mean_concat(x, adj: CsrMatrix, out=None):
     """h = cat([x, mean_{j in N(i)} x_j]); reference src/corrector_model.py:23-30."""
     x = _check(_rowmajor(x))
     n, d = x.shape
-    H = torch.empty((n, 2 * d), device=x.device, dtype=torch.float32)
+    H = out if out is not None else torch.empty((n, 2 * d), device=x.device, dtype=torch.float32)
     call("ep_neighbor_mean_concat_f32", n, d, _ptr(adj.rowptr), _ptr(adj.col), _ptr(x), x.stride(0), _ptr(H),
          H.stride(0), _stream())
     return H
 
 
-def spmm_concat(x, A: CsrMatrix):
+def spmm_concat(x, A: CsrMatrix, out=None):
     """h = cat([x, A x]); reference src/corrector_model.py:76-79."""
     x = _check(_rowmajor(x))
     n, d = x.shape
-    H = torch.empty((n, 2 * d), device=x.device, dtype=torch.float32)
+    H = out if out is not None else torch.empty((n, 2 * d), device=x.device, dtype=torch.float32)
     call("ep_spmm_concat_f32", n, d, _ptr(A.rowptr), _ptr(A.col), _ptr(A.val), _ptr(x), x.stride(0), _ptr(H),
          H.stride(0), _stream())
     return H
