@@ -92,7 +92,7 @@ def read_vtu_point_data(vtu_file):
                          text):
         dtype, name, payload = m.group(1), m.group(2), m.group(3).strip()
         hs = np.dtype(head_t).itemsize
-        nb = int(np.frombuffer(base64.b64decode(payload[:_b64len(hs)]), dtype=head_t)[0])
+        nb = int(np.frombuffer(base64.b64decode(payload[:_b64len(hs)])[:hs], dtype=head_t)[0])
         head_len = _b64len(hs * (3 + nb))
         head = np.frombuffer(base64.b64decode(payload[:head_len]), dtype=head_t)
         data = base64.b64decode(payload[head_len:])
