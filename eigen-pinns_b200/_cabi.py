@@ -20,7 +20,7 @@ SIGNATURES = {
     "ep_device_info": (c_int, [c_p, c_p, c_p]),
     "ep_spmm_csr_f32": (c_int, [c_int, c_int, c_p, c_p, c_p, c_p, c_int, c_p, c_int, c_p]),
     "ep_spmm2_csr_f32": (c_int, [c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_int, c_p, c_p, c_int, c_p]),
-    "ep_spmm2_sum_csr_f32": (c_int, [c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_p, c_int, c_f,
+    "ep_spmm2_sum_csr_f32": (c_int, [c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_p, c_int, c_f, c_p,
                                      c_p, c_int, c_p]),
     "ep_neighbor_mean_concat_f32": (c_int, [c_int, c_int, c_p, c_p, c_p, c_int, c_p, c_int, c_p]),
     "ep_spmm_concat_f32": (c_int, [c_int, c_int, c_p, c_p, c_p, c_p, c_int, c_p, c_int, c_p]),
@@ -30,7 +30,7 @@ SIGNATURES = {
     "ep_eigen_coef_len": (c_sz, [c_int]),
     "ep_eigen_finalize_f32": (c_int, [c_int, c_d, c_p, c_f, c_f, c_int, c_p, c_f, c_f, c_f, c_p, c_p, c_p, c_p, c_p]),
     "ep_eigen_bwd_prepare_f32": (c_int, [c_int, c_int, c_p, c_int, c_p, c_p, c_int, c_p, c_p, c_p, c_p, c_p]),
-    "ep_eigen_bwd_fused_sym_f32": (c_int, [c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_p, c_f, c_p, c_int, c_p]),
+    "ep_eigen_bwd_fused_sym_f32": (c_int, [c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_p, c_f, c_p, c_p, c_int, c_p]),
     "ep_scale_columns_rsqrt_f32": (c_int, [c_int, c_int, c_p, c_int, c_p, c_int, c_d, c_p, c_int, c_p]),
     "ep_axpy_out_f32": (c_int, [c_sz, c_f, c_p, c_p, c_p, c_p, c_p]),
     "ep_linear_fwd_f32": (c_int, [c_int, c_int, c_int, c_p, c_int, c_p, c_p, c_p, c_int, c_int, c_p]),

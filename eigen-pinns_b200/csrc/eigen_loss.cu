@@ -408,8 +408,9 @@ __global__ void __launch_bounds__(256)
 eigen_bwd_fused_sym_kernel(int n, int k, int lpr_shift, const int32_t* __restrict__ rowptr,
                            const int32_t* __restrict__ col, const float* __restrict__ valK,
                            const float* __restrict__ valM, const float* __restrict__ KU,
-                           const float* __restrict__ MU, int ld, const float* __restrict__ coef, float out_scale,
-                           float* __restrict__ dU, int ldo) {
+                           const float* __restrict__ MU, int ld, const float* __restrict__ coef, float out_scale_v,
+                           const float* __restrict__ out_scale_dev, float* __restrict__ dU, int ldo) {
+  const float out_scale = out_scale_dev ? __ldg(out_scale_dev) : out_scale_v;
   extern __shared__ __align__(16) float fsm[];
   float* S = fsm;                 // k x k
   float* s_lam = S + k * k;       // k
@@ -614,7 +615,7 @@ int ep_eigen_bwd_prepare_f32(int n, int k, const float* U, int ldu, const float*
 
 int ep_eigen_bwd_fused_sym_f32(int n, int k, const int32_t* rowptr, const int32_t* col, const float* valK,
                                const float* valM, const float* KU, const float* MU, int ld, const float* coef,
-                               float out_scale, float* dU, int ldo, ep_stream_t stream) {
+                               float out_scale, const float* out_scale_dev, float* dU, int ldo, ep_stream_t stream) {
   EP_REQUIRE(n >= 0 && k > 0, "bad size");
   if (n == 0) return EP_OK;
   EP_REQUIRE(rowptr && col && valK && valM && KU && MU && coef && dU, "null pointer");
@@ -639,7 +640,7 @@ int ep_eigen_bwd_fused_sym_f32(int n, int k, const int32_t* rowptr, const int32_
   if (grid > cap) grid = cap;
   cudaStream_t st = ep::as_stream(stream);
 #define EP_FUSED_LAUNCH(KVT) eigen_bwd_fused_sym_kernel<KVT><<<(unsigned)grid, 256, smem, st>>>( \
-      n, k, lpr_shift, rowptr, col, valK, valM, KU, MU, ld, coef, out_scale, dU, ldo)
+      n, k, lpr_shift, rowptr, col, valK, valM, KU, MU, ld, coef, out_scale, out_scale_dev, dU, ldo)
   switch (kv) {
     case 4: EP_FUSED_LAUNCH(4); break;
     case 8: EP_FUSED_LAUNCH(8); break;

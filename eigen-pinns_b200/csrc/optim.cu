@@ -38,17 +38,19 @@ __global__ void sqnorm_final_kernel(int n_parts, double* __restrict__ out) {
 
 __global__ void __launch_bounds__(256)
 adam_clip_kernel(size_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                 float* __restrict__ v, float lr, const float* __restrict__ lr_dev, float beta1, float beta2,
-                 float eps, float wd, double bc1, double bc2_sqrt, float max_norm,
+                 float* __restrict__ v, float lr, const float* __restrict__ hyper_dev, float beta1, float beta2,
+                 float eps, float wd, double bc1_v, double bc2_sqrt_v, float max_norm,
                  const double* __restrict__ sq_norm) {
   float coef = 1.0f;
   if (sq_norm != nullptr && max_norm > 0.f) {
     const float total = (float)sqrt(*sq_norm);
     coef = fminf(max_norm / (total + 1e-6f), 1.0f);
   }
-  const float lr_now = lr_dev ? *lr_dev : lr;
+  // hyper_dev = {lr, 1 - beta1^t, sqrt(1 - beta2^t)} in device memory (CUDA-graph replay), else by value
+  const float lr_now = hyper_dev ? hyper_dev[0] : lr;
+  const double bc1 = hyper_dev ? (double)hyper_dev[1] : bc1_v;
   const float step_size = (float)((double)lr_now / bc1);
-  const float bc2s = (float)bc2_sqrt;
+  const float bc2s = hyper_dev ? hyper_dev[2] : (float)bc2_sqrt_v;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float pi = p[i];
     float gi = g[i] * coef;
@@ -78,18 +80,18 @@ int ep_grad_sqnorm_f32(size_t n, const float* g, double* sq_out, ep_stream_t str
   return EP_OK;
 }
 
-int ep_adam_clip_step_f32(size_t n, float* p, const float* g, float* m, float* v, float lr, const float* lr_dev,
+int ep_adam_clip_step_f32(size_t n, float* p, const float* g, float* m, float* v, float lr, const float* hyper_dev,
                           float beta1, float beta2, float eps, float weight_decay, int step, float max_norm,
                           const double* sq_norm, ep_stream_t stream) {
   if (n == 0) return EP_OK;
   EP_REQUIRE(p && g && m && v, "null pointer");
-  EP_REQUIRE(step >= 1, "step counts from 1");
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2_sqrt = sqrt(1.0 - pow((double)beta2, (double)step));
+  EP_REQUIRE(step >= 1 || hyper_dev, "step counts from 1");
+  const double bc1 = 1.0 - pow((double)beta1, (double)(step >= 1 ? step : 1));
+  const double bc2_sqrt = sqrt(1.0 - pow((double)beta2, (double)(step >= 1 ? step : 1)));
   size_t grid = (n + 255) / 256;
   const size_t cap = (size_t)ep::sm_count() * 8;
   if (grid > cap) grid = cap;
-  adam_clip_kernel<<<(unsigned)grid, 256, 0, ep::as_stream(stream)>>>(n, p, g, m, v, lr, lr_dev, beta1, beta2, eps,
+  adam_clip_kernel<<<(unsigned)grid, 256, 0, ep::as_stream(stream)>>>(n, p, g, m, v, lr, hyper_dev, beta1, beta2, eps,
                                                                      weight_decay, bc1, bc2_sqrt, max_norm, sq_norm);
   EP_LAUNCH_CHECK("adam_clip_kernel");
   return EP_OK;

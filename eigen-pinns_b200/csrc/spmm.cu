@@ -51,7 +51,8 @@ spmm_kernel(int n_rows, int kv, int lpr_shift, const int32_t* __restrict__ rowpt
             const int32_t* __restrict__ col, const float* __restrict__ valA,
             const float* __restrict__ valB, const float* __restrict__ XA,
             const float* __restrict__ XB, int ldx, const float* __restrict__ D, int ldd,
-            float out_scale, float* __restrict__ YA, float* __restrict__ YB, int ldy) {
+            float out_scale, const float* __restrict__ out_scale_dev, float* __restrict__ YA,
+            float* __restrict__ YB, int ldy) {
   using T = typename VecT<V>::type;
   const int lpr = 1 << lpr_shift;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -94,7 +95,7 @@ spmm_kernel(int n_rows, int kv, int lpr_shift, const int32_t* __restrict__ rowpt
     if (MODE == 2) {
       if (D != nullptr)
         accA = vadd(accA, __ldg(reinterpret_cast<const T*>(D + (size_t)row * ldd + (size_t)cv * V)));
-      accA = vscale(accA, out_scale);
+      accA = vscale(accA, out_scale_dev ? __ldg(out_scale_dev) : out_scale);
     }
     *reinterpret_cast<T*>(YA + (size_t)row * ldy + (size_t)cv * V) = accA;
     if (MODE == 1) *reinterpret_cast<T*>(YB + (size_t)row * ldy + (size_t)cv * V) = accB;
@@ -104,7 +105,7 @@ spmm_kernel(int n_rows, int kv, int lpr_shift, const int32_t* __restrict__ rowpt
 template <int MODE>
 int launch_spmm(int n_rows, int k, const int32_t* rowptr, const int32_t* col, const float* valA,
                 const float* valB, const float* XA, const float* XB, int ldx, const float* D, int ldd,
-                float out_scale, float* YA, float* YB, int ldy, cudaStream_t st) {
+                float out_scale, const float* out_scale_dev, float* YA, float* YB, int ldy, cudaStream_t st) {
   if (n_rows == 0 || k == 0) return EP_OK;
   int V = 1;
   auto ok_for = [&](int v) {
@@ -126,7 +127,7 @@ int launch_spmm(int n_rows, int k, const int32_t* rowptr, const int32_t* col, co
   if (grid > 0x7fffffffLL) { ep::set_error("spmm: grid too large"); return EP_ERR_UNSUPPORTED; }
 #define EP_SPMM_LAUNCH(VV)                                                                      \
   spmm_kernel<VV, MODE><<<(unsigned)grid, block, 0, st>>>(n_rows, kv, lpr_shift, rowptr, col,   \
-      valA, valB, XA, XB, ldx, D, ldd, out_scale, YA, YB, ldy)
+      valA, valB, XA, XB, ldx, D, ldd, out_scale, out_scale_dev, YA, YB, ldy)
   if (V == 4) EP_SPMM_LAUNCH(4); else if (V == 2) EP_SPMM_LAUNCH(2); else EP_SPMM_LAUNCH(1);
 #undef EP_SPMM_LAUNCH
   EP_LAUNCH_CHECK("spmm_kernel");
@@ -194,7 +195,7 @@ int ep_spmm_csr_f32(int n_rows, int k, const int32_t* rowptr, const int32_t* col
   EP_REQUIRE(n_rows >= 0 && k >= 0, "negative size");
   EP_REQUIRE(rowptr && (n_rows == 0 || (col && val && X && Y)), "null pointer");
   EP_REQUIRE(ldx >= k && ldy >= k, "leading dimension < k");
-  return launch_spmm<0>(n_rows, k, rowptr, col, val, nullptr, X, nullptr, ldx, nullptr, 0, 1.f, Y,
+  return launch_spmm<0>(n_rows, k, rowptr, col, val, nullptr, X, nullptr, ldx, nullptr, 0, 1.f, nullptr, Y,
                         nullptr, ldy, ep::as_stream(stream));
 }
 
@@ -204,18 +205,18 @@ int ep_spmm2_csr_f32(int n_rows, int k, const int32_t* rowptr, const int32_t* co
   EP_REQUIRE(n_rows >= 0 && k >= 0, "negative size");
   EP_REQUIRE(rowptr && (n_rows == 0 || (col && valA && valB && X && YA && YB)), "null pointer");
   EP_REQUIRE(ldx >= k && ldy >= k, "leading dimension < k");
-  return launch_spmm<1>(n_rows, k, rowptr, col, valA, valB, X, nullptr, ldx, nullptr, 0, 1.f, YA, YB,
+  return launch_spmm<1>(n_rows, k, rowptr, col, valA, valB, X, nullptr, ldx, nullptr, 0, 1.f, nullptr, YA, YB,
                         ldy, ep::as_stream(stream));
 }
 
 int ep_spmm2_sum_csr_f32(int n_rows, int k, const int32_t* rowptr, const int32_t* col,
                          const float* valA, const float* valB, const float* XA, const float* XB,
-                         int ldx, const float* D, int ldd, float out_scale, float* Y, int ldy,
-                         ep_stream_t stream) {
+                         int ldx, const float* D, int ldd, float out_scale, const float* out_scale_dev, float* Y,
+                         int ldy, ep_stream_t stream) {
   EP_REQUIRE(n_rows >= 0 && k >= 0, "negative size");
   EP_REQUIRE(rowptr && (n_rows == 0 || (col && valA && valB && XA && XB && Y)), "null pointer");
   EP_REQUIRE(ldx >= k && ldy >= k && (!D || ldd >= k), "leading dimension < k");
-  return launch_spmm<2>(n_rows, k, rowptr, col, valA, valB, XA, XB, ldx, D, ldd, out_scale, Y, nullptr,
+  return launch_spmm<2>(n_rows, k, rowptr, col, valA, valB, XA, XB, ldx, D, ldd, out_scale, out_scale_dev, Y, nullptr,
                         ldy, ep::as_stream(stream));
 }
 
@@ -241,7 +242,7 @@ int ep_spmm_concat_f32(int n, int d, const int32_t* rowptr, const int32_t* col, 
   cudaStream_t st = ep::as_stream(stream);
   copy2d_kernel<<<grid_for((long long)n * d, 256), 256, 0, st>>>(n, d, x, ldx, H, ldh);
   EP_LAUNCH_CHECK("copy2d_kernel");
-  return launch_spmm<0>(n, d, rowptr, col, val, nullptr, x, nullptr, ldx, nullptr, 0, 1.f, H + d,
+  return launch_spmm<0>(n, d, rowptr, col, val, nullptr, x, nullptr, ldx, nullptr, 0, 1.f, nullptr, H + d,
                         nullptr, ldh, st);
 }
 

@@ -30,12 +30,16 @@ class HaloExchanger:
         self.plan, self.group, self.gather = plan, group, gather
         self.send_idx = {p: torch.from_numpy(ix).to(device) for p, ix in sorted(plan.send.items())}
         self.recv = dict(sorted(plan.recv.items()))
+        self._bufs = {}                     # (peer, k) -> preallocated send buffer (stable under graph capture)
 
     def exchange(self, rows, n_own):
         """rows: (n_own + n_halo) x k tensor; fills rows[n_own:] from the owners."""
         reqs, keep = [], []
         for p, idx in self.send_idx.items():
-            buf = self.gather(rows, idx)
+            key = (p, rows.shape[1])
+            if key not in self._bufs:
+                self._bufs[key] = torch.empty((idx.numel(), rows.shape[1]), dtype=rows.dtype, device=rows.device)
+            buf = self.gather(rows, idx, self._bufs[key])
             keep.append(buf)
             reqs.append(dist.P2POp(dist.isend, buf, p, self.group))
         for p, (off, cnt) in self.recv.items():
@@ -71,7 +75,7 @@ class ShardedTrainStepEngine(TrainStepEngine):
             off += pl.n_own + pl.n_halo
         assert off == h_local.shape[0] == U_base_local.shape[0]
         super().__init__(h_local, U_base_local, pairs, offsets, params, cfg, lam_target, mlp_mode)
-        self.halo = [HaloExchanger(pl, dev, lambda rows, idx: ops.gather_rows(rows, idx), group) for pl in plans]
+        self.halo = [HaloExchanger(pl, dev, lambda rows, idx, out: ops.gather_rows(rows, idx, out=out), group) for pl in plans]
         self.dCorr.zero_()                      # halo rows never receive a gradient on this rank
 
     def _ext(self, buf, li):

@@ -68,14 +68,14 @@ class Fp32Mlp:
         wmax = max(dims[1:-1]) if len(dims) > 2 else dims[0]
         self.dx = [torch.empty((n, wmax), dtype=torch.float32, device=device) for _ in range(2)]
 
-    def forward(self, h, U_base=None, scale=0.0, U_pred=None):
+    def forward(self, h, U_base=None, scale=0.0, U_pred=None, scale_dev=None):
         x = h
         L = len(self.p.W)
         for l in range(L):
             ops.linear_fwd(x, self.p.W[l], self.p.b[l], relu=(l < L - 1), out=self.acts[l])
             x = self.acts[l]
         if U_pred is not None:
-            ops.axpy_out(U_base, x, scale, out=U_pred)
+            ops.axpy_out(U_base, x, scale, out=U_pred, alpha_dev=scale_dev)
         return x                                    # corr_raw (n x k)
 
     def backward(self, h, d_out):
@@ -132,14 +132,15 @@ class TrainStepEngine:
         else:
             raise ValueError("mlp_mode must be 'fp32' or 'bf16'")
         self.launches_per_step = None
+        self.use_graph, self._graph, self.hyper = False, None, None
         self.fused_bwd = True          # symmetric operators: one-pass analytic backward
 
     # ---- pieces (also used one by one by the tests)
     def scale_for(self, epoch):
         return self.cfg.corr_scale * min(1.0, epoch / self.cfg.ramp_epochs)
 
-    def forward(self, scale):
-        return self.mlp.forward(self.h, U_base=self.U_base, scale=scale, U_pred=self.U_pred)
+    def forward(self, scale, scale_dev=None):
+        return self.mlp.forward(self.h, U_base=self.U_base, scale=scale, U_pred=self.U_pred, scale_dev=scale_dev)
 
     def _level_slices(self, li):
         off, n = self.offsets[li], self.pairs[li].n
@@ -157,23 +158,25 @@ class TrainStepEngine:
                                coef=self.coefs[li], lam_out=self.lams[li], level0=(li == 0),
                                lam_target=self.lam_target, w_trace=c.w_trace, w_order=c.w_order, w_eigen=c.w_eigen)
 
-    def loss_backward(self, scale):
+    def loss_backward(self, scale, scale_dev=None):
         for li, pair in enumerate(self.pairs):
             s = self._level_slices(li)
             if self.fused_bwd and ops.eigen_bwd_fused_ok(pair, self.k, self.KU[s], self.MU[s], self.dCorr[s]):
-                ops.eigen_bwd_fused(pair, self.KU[s], self.MU[s], self.coefs[li], scale, self.dCorr[s])
+                ops.eigen_bwd_fused(pair, self.KU[s], self.MU[s], self.coefs[li], scale, self.dCorr[s], scale_dev)
                 continue
             ops.eigen_bwd_prepare(self.U_pred[s], self.KU[s], self.MU[s], self.coefs[li], self.KU_bar[s],
                                   self.MU_bar[s], self.D[s])
-            ops.spmm2_sum(pair.KT, pair.MT, self.KU_bar[s], self.MU_bar[s], self.D[s], scale, out=self.dCorr[s])
+            ops.spmm2_sum(pair.KT, pair.MT, self.KU_bar[s], self.MU_bar[s], self.D[s], scale, out=self.dCorr[s],
+                          scale_dev=scale_dev)
 
-    def optimizer_step(self, lr):
+    def optimizer_step(self, lr, hyper_dev=None):
         p, c = self.params, self.cfg
         self._reduce_grads()
         ops.grad_sqnorm(p.grad, p.sq_norm)
-        p.step_count += 1
-        ops.adam_clip_step(p.flat, p.grad, p.m, p.v, lr, c.beta1, c.beta2, c.eps, c.weight_decay, p.step_count,
-                           c.grad_clip, p.sq_norm)
+        if hyper_dev is None:
+            p.step_count += 1
+        ops.adam_clip_step(p.flat, p.grad, p.m, p.v, lr, c.beta1, c.beta2, c.eps, c.weight_decay,
+                           max(p.step_count, 1), c.grad_clip, p.sq_norm, hyper_dev)
 
     # hooks for the vertex-sharded engine
     def _n_global(self, li):
@@ -189,6 +192,9 @@ class TrainStepEngine:
         """One epoch body.  Returns the device tensor loss_acc = [res, orth, trace, order, eigen, total]
         (weighted, fp64); reading it on the host is the caller's one sync per step.
         marks: optional list that receives (phase, cuda event) pairs recorded on the current stream."""
+        if self.use_graph and marks is None:
+            return self._step_graph(epoch, self.cfg.lr if lr is None else lr)
+
         def mark(name):
             if marks is not None:
                 ev = torch.cuda.Event(enable_timing=True)
@@ -207,6 +213,53 @@ class TrainStepEngine:
         self.optimizer_step(self.cfg.lr if lr is None else lr)
         mark("optim")
         return self.loss_acc
+
+    # ---- CUDA-graph replay: the whole step is captured once; per-step scalars live in device memory
+    def _write_hyper(self, epoch, lr):
+        c, p = self.cfg, self.params
+        t = p.step_count + 1
+        slot = self._hyper_slot = (self._hyper_slot + 1) % len(self._hyper_host)
+        self._hyper_evt[slot].synchronize()          # the upload that last used this pinned slot has finished
+        host = self._hyper_host[slot]
+        host[0] = self.scale_for(epoch)
+        host[1] = lr
+        host[2] = 1.0 - c.beta1 ** t
+        host[3] = (1.0 - c.beta2 ** t) ** 0.5
+        self.hyper.copy_(host, non_blocking=True)
+        self._hyper_evt[slot].record()
+
+    def _step_body_dev(self):
+        sd = self.hyper[0:1]
+        self.forward(0.0, scale_dev=sd)
+        self.loss_forward()
+        self.loss_backward(0.0, scale_dev=sd)
+        self.mlp.backward(self.h, self.dCorr)
+        self.optimizer_step(0.0, hyper_dev=self.hyper[1:4])
+
+    def _step_graph(self, epoch, lr):
+        if self.hyper is None:
+            self.hyper = torch.zeros(4, dtype=torch.float32, device=self.dev)
+            self._hyper_host = [torch.zeros(4, dtype=torch.float32).pin_memory() for _ in range(16)]
+            self._hyper_evt = [torch.cuda.Event() for _ in range(16)]
+            self._hyper_slot = -1
+        self._write_hyper(epoch, lr)
+        if self._graph is None:
+            from . import _cabi
+            torch.cuda.synchronize()
+            before = _cabi.launch_counter
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_body_dev()
+            self.launches_per_step = _cabi.launch_counter - before
+            self._graph = g
+        self._graph.replay()
+        self.params.step_count += 1
+        return self.loss_acc
+
+    def enable_graph(self, on=True):
+        """Replay the step as one CUDA graph (call after a few eager warm-up steps).  Changing the shape of the
+        problem or the input tensor objects requires enable_graph() again to re-capture."""
+        self.use_graph, self._graph = bool(on), None
 
     def step_from_host(self, h_host, U_base_host, epoch, lr=None):
         """Simplest end-to-end variant: this step's corrector input and base subspace arrive in (pinned) host

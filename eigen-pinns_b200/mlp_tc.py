@@ -75,7 +75,7 @@ class TcMlp:
             call("ep_tc_pack_weight_bf16", W.shape[0], W.shape[1], self.pd[l + 1], self.pd[l], _p(W), _p(self.Wp[l]),
                  _p(self.WTp[l]) if l > 0 else None, _stream())
 
-    def forward(self, h, U_base=None, scale=0.0, U_pred=None):
+    def forward(self, h, U_base=None, scale=0.0, U_pred=None, scale_dev=None):
         if self._packed_version != (h.data_ptr(), h._version):
             self.input_changed(h)
         self._pack_weights()
@@ -86,7 +86,7 @@ class TcMlp:
             x = self.acts[l]
         l = self.L - 1
         call("ep_tc_linear_final_bf16", self.n, self.pd[l], self.dims[-1], self.pd[-1], _p(x), _p(self.Wp[l]),
-             _p(self.p.b[l]), _p(self.corr), self.corr.stride(0), _p(U_base), float(scale), None, _p(U_pred),
+             _p(self.p.b[l]), _p(self.corr), self.corr.stride(0), _p(U_base), float(scale), _p(scale_dev), _p(U_pred),
              U_pred.stride(0) if U_pred is not None else 0, _stream())
         return self.corr
 

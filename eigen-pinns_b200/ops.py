@@ -60,7 +60,7 @@ def spmm2(pair: OperatorPair, X, out_K=None, out_M=None):
     return KU, MU
 
 
-def spmm2_sum(KT: CsrMatrix, MT: CsrMatrix, XA, XB, D=None, scale=1.0, out=None):
+def spmm2_sum(KT: CsrMatrix, MT: CsrMatrix, XA, XB, D=None, scale=1.0, out=None, scale_dev=None):
     """out = scale * (KT XA + MT XB + D); KT and MT share a pattern."""
     XA, XB = _check(XA), _check(XB)
     k = XA.shape[1]
@@ -68,7 +68,7 @@ def spmm2_sum(KT: CsrMatrix, MT: CsrMatrix, XA, XB, D=None, scale=1.0, out=None)
     Y = out if out is not None else torch.empty((KT.shape[0], k), device=XA.device, dtype=torch.float32)
     call("ep_spmm2_sum_csr_f32", KT.shape[0], k, _ptr(KT.rowptr), _ptr(KT.col), _ptr(KT.val), _ptr(MT.val),
          _ptr(XA), _ptr(XB), XA.stride(0), _ptr(D), D.stride(0) if D is not None else 0,
-         float(scale), _ptr(Y), Y.stride(0), _stream())
+         float(scale), _ptr(scale_dev), _ptr(Y), Y.stride(0), _stream())
     return Y
 
 
@@ -169,12 +169,13 @@ def eigen_bwd_fused_ok(pair, k, *tensors):
             and all(t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in tensors))
 
 
-def eigen_bwd_fused(pair, KU, MU, coef, scale, out):
+def eigen_bwd_fused(pair, KU, MU, coef, scale, out, scale_dev=None):
     """dL/dU for symmetric (K, M) in one gather pass (see ep_eigen_bwd_fused_sym_f32)."""
     n, k = KU.shape
     assert KU.stride(0) == MU.stride(0)
     call("ep_eigen_bwd_fused_sym_f32", n, k, _ptr(pair.K.rowptr), _ptr(pair.K.col), _ptr(pair.K.val), _ptr(pair.M.val),
-         _ptr(KU), _ptr(MU), KU.stride(0), _ptr(coef), float(scale), _ptr(out), out.stride(0), _stream())
+         _ptr(KU), _ptr(MU), KU.stride(0), _ptr(coef), float(scale), _ptr(scale_dev), _ptr(out), out.stride(0),
+         _stream())
     return out
 
 
@@ -334,8 +335,9 @@ def grad_sqnorm(g, out):
     return out
 
 
-def adam_clip_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, max_norm, sq_norm, lr_dev=None):
-    call("ep_adam_clip_step_f32", p.numel(), _ptr(p), _ptr(g), _ptr(m), _ptr(v), float(lr), _ptr(lr_dev),
+def adam_clip_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, max_norm, sq_norm, hyper_dev=None):
+    """hyper_dev: device tensor {lr, 1 - beta1^t, sqrt(1 - beta2^t)} overriding lr / step (graph replay)."""
+    call("ep_adam_clip_step_f32", p.numel(), _ptr(p), _ptr(g), _ptr(m), _ptr(v), float(lr), _ptr(hyper_dev),
          float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(max_norm), _ptr(sq_norm),
          _stream())
 

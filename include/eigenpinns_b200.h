@@ -64,13 +64,14 @@ EP_API int ep_spmm_csr_f32(int n_rows, int k, const int32_t* rowptr, const int32
 EP_API int ep_spmm2_csr_f32(int n_rows, int k, const int32_t* rowptr, const int32_t* col,
                      const float* valA, const float* valB, const float* X, int ldx,
                      float* YA, float* YB, int ldy, ep_stream_t stream);
-/* Y = out_scale * (A XA + B XB + D)   (D may be NULL).  Backward of the eigen-loss:
+/* Y = out_scale * (A XA + B XB + D)   (D may be NULL; out_scale_dev, a device scalar, overrides out_scale
+ * when non-NULL so that a captured CUDA graph can follow the epoch-dependent scale ramp).  Backward of the eigen-loss:
  * U_bar = K^T KU_bar + M^T MU_bar + D; pass the CSR of the transposes
  * (identical to K, M for the symmetric FEM / tufted operators). */
 EP_API int ep_spmm2_sum_csr_f32(int n_rows, int k, const int32_t* rowptr, const int32_t* col,
                          const float* valA, const float* valB, const float* XA, const float* XB,
-                         int ldx, const float* D, int ldd, float out_scale, float* Y, int ldy,
-                         ep_stream_t stream);
+                         int ldx, const float* D, int ldd, float out_scale, const float* out_scale_dev,
+                         float* Y, int ldy, ep_stream_t stream);
 
 /* ---- corrector input: h = cat([x, agg], dim=1) -----------------------------------------
  * SimpleCorrector.forward, corrector_model.py:23-30: agg_i = (sum over edges (i<-j) of x_j) /
@@ -135,7 +136,8 @@ EP_API int ep_eigen_bwd_prepare_f32(int n, int k, const float* U, int ldu, const
  * M = M^T.  Needs k % 4 == 0, k <= 128, 16-byte aligned rows (EP_ERR_UNSUPPORTED otherwise). */
 EP_API int ep_eigen_bwd_fused_sym_f32(int n, int k, const int32_t* rowptr, const int32_t* col, const float* valK,
                                const float* valM, const float* KU, const float* MU, int ld, const float* coef,
-                               float out_scale, float* dU, int ldo, ep_stream_t stream);
+                               float out_scale, const float* out_scale_dev, float* dU, int ldo,
+                               ep_stream_t stream);
 
 /* ---- column M-normalisation: multigrid_model.py:120-130, :366-380 ----------------------
  * out[:, j] = U[:, j] / sqrt(colsum_j + 1e-12) where colsum_j = sum_i U_ij MU_ij is read from
@@ -208,11 +210,11 @@ EP_API int ep_tc_linear_dw_bf16(int n, int out, int in, int out_padded, int in_p
  *   coef   = min(1, max_norm / (norm + 1e-6));  g = coef * g + weight_decay * p
  *   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2
  *   p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
- * lr_dev (device scalar, may be NULL) overrides lr so a captured graph can follow the
- * ReduceLROnPlateau schedule of :221-223. */
+ * hyper_dev (device, may be NULL) = {lr, 1 - b1^t, sqrt(1 - b2^t)} overrides lr and the step-dependent
+ * bias corrections, so a captured CUDA graph can follow the ReduceLROnPlateau schedule of :221-223. */
 EP_API int ep_grad_sqnorm_f32(size_t n, const float* g, double* sq_out, ep_stream_t stream);
 EP_API int ep_adam_clip_step_f32(size_t n, float* p, const float* g, float* m, float* v, float lr,
-                          const float* lr_dev, float beta1, float beta2, float eps,
+                          const float* hyper_dev, float beta1, float beta2, float eps,
                           float weight_decay, int step, float max_norm, const double* sq_norm,
                           ep_stream_t stream);
 

@@ -154,3 +154,28 @@ def test_adam_clip_kernel_vs_torch():
         ops.grad_sqnorm(gd, sq)
         ops.adam_clip_step(p, gd, m, v, 1e-3, 0.9, 0.999, 1e-8, 1e-5, step, 10.0, sq)
         np.testing.assert_allclose(p.cpu().numpy(), ref.detach().numpy(), rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("mlp_mode", ["fp32", "bf16"])
+def test_cuda_graph_replay_equals_eager(mlp_mode):
+    """The captured step (scalars read from device memory) must reproduce the eager step exactly."""
+    runs = []
+    for graphed in (False, True):
+        gnn, g, fem, (K, M), (Kc, Mc) = _golden_trainer("simple", mlp_mode)
+        x = torch.from_numpy(g["simple_x_feats"]).to(dev())
+        ei = torch.from_numpy(g["edge_index_all"])
+        gnn._initialize_model(x.shape[1], 16, gnn.hidden_layers, 0.0)
+        gnn.model.load_state_dict({k_[12:]: torch.from_numpy(g[k_]) for k_ in g.files if k_.startswith("simple_init_")})
+        opt, _ = gnn._create_optimizer(gnn.lr, gnn.weight_decay)
+        U_all = torch.cat([torch.from_numpy(g["U_norm_0"]), torch.from_numpy(g["U_norm_1"])])
+        eng = gnn._make_engine(x, ei, None, U_all, [Kc, K], [Mc, M], torch.from_numpy(g["lam_0"]),
+                               [0, g["U_norm_0"].shape[0]], opt)
+        hist = [eng.step(2500).cpu().numpy().copy()]
+        if graphed:
+            eng.enable_graph()
+        for e in range(2501, 2512):
+            lr = 1e-3 if e < 2506 else 5e-4                       # the schedule may change the rate between replays
+            hist.append(eng.step(e, lr=lr).cpu().numpy().copy())
+        runs.append((np.array(hist), eng.params.flat.clone()))
+    np.testing.assert_allclose(runs[0][0], runs[1][0], rtol=1e-6 if mlp_mode == "fp32" else 1e-5)
+    assert (runs[0][1] - runs[1][1]).abs().max().item() <= 1e-6

@@ -60,7 +60,7 @@ def _worker(rank, world, port, out_dir):
         plan = de.resolve_send_lists(partition.LevelPlan(K, M, rank, world))
         rows = torch.zeros(plan.n_own + plan.n_halo, k)
         rows[:plan.n_own] = torch.from_numpy(U[plan.lo:plan.hi])
-        ex = de.HaloExchanger(plan, torch.device("cpu"), lambda r, idx: r.index_select(0, idx.long()))
+        ex = de.HaloExchanger(plan, torch.device("cpu"), lambda r, idx, out: torch.index_select(r, 0, idx.long(), out=out))
         ex.exchange(rows, plan.n_own)
         assert np.array_equal(rows[plan.n_own:].numpy(), U[plan.halo_global])
         KU_loc = plan.K_local.astype(np.float32) @ rows.numpy()
