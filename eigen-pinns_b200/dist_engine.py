@@ -97,11 +97,11 @@ class ShardedTrainStepEngine(TrainStepEngine):
             self.halo[li].exchange(self._ext(self.U_pred, li), pl.n_own)
         super().loss_forward()
 
-    def loss_backward(self, scale):
+    def loss_backward(self, scale, scale_dev=None):
         for li, pl in enumerate(self.plans):
             self.halo[li].exchange(self._ext(self.KU, li), pl.n_own)
             self.halo[li].exchange(self._ext(self.MU, li), pl.n_own)
-        super().loss_backward(scale)
+        super().loss_backward(scale, scale_dev=scale_dev)
 
 
 def shard_rows(global_rows, plans, global_offsets):

@@ -41,11 +41,14 @@ def main():
             eng = de.make_sharded_engine(gnn, x_feats, edge_all, U_norm[0], w["K"], w["M"], lam0, opt, rank, world)
         else:
             eng = gnn._make_engine(x_feats, edge_all, A_norm, U_norm[0], [w["K"]], [w["M"]], lam0, [0], opt)
-        losses = [eng.step(2500 + i).cpu().numpy().copy() for i in range(4)]
+        losses = [eng.step(2500 + i).cpu().numpy().copy() for i in range(2)]
+        if sharded and len(sys.argv) > 2 and sys.argv[2] == "graph":
+            eng.enable_graph()
+        losses += [eng.step(2502 + i).cpu().numpy().copy() for i in range(2)]
         results.append((np.array(losses), eng.params.flat.clone(), [l.clone() for l in eng.lams]))
     sys.stdout = sys.__stdout__
     (l1, p1, lam1), (l2, p2, lam2) = results
-    tol = 1e-5 if mode == "fp32" else 2e-3
+    tol = 1e-4 if mode == "fp32" else 2e-3
     ok = np.allclose(l1, l2, rtol=tol, atol=1e-9)
     perr = (p1 - p2).abs().max().item()
     ok = ok and perr <= (2e-5 if mode == "fp32" else 2e-3)
