@@ -319,6 +319,25 @@ def run_ours(args):
         n_pad = (m.n + 127) // 128 * 128
         hidden_bytes = n_pad * (m.pd[1] + m.pd[2]) * 2 + n_pad * (m.pd[2] // 8)
 
+    # ---- samplers at BASELINE config 3 size (1 M-point cloud): FPS iterations and one voxel hierarchy
+    samplers_info = None
+    if world == 1 and not args.no_samplers:
+        sampling = pkg("sampling")
+        cloud = torch.from_numpy(np.random.default_rng(1234).standard_normal((1_000_000, 3))).to(dev)
+        sampling.fps_order(cloud, 64, 7)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sampling.fps_order(cloud, 1024, 7)
+        torch.cuda.synchronize()
+        fps_ms = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter()
+        sampling.voxel_levels(cloud, [256, 512, 1024])
+        vox_ms = (time.perf_counter() - t0) * 1e3
+        samplers_info = {"points": 1000000, "fps_1024_samples_ms": fps_ms, "fps_us_per_iteration": fps_ms * 1e3 / 1023,
+                         "voxel_hierarchy_256_512_1024_ms": vox_ms,
+                         "reference_cpu": "43.4 ms per FPS iteration, 1.25 s per voxel level (SURVEY 6, 8 cores)"}
+        del cloud
+
     # ---- host issue time (how long Python + ctypes take to enqueue one step)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -403,7 +422,7 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (U, KU, MU, activations >> 126 MB)"},
             "clocks": clk, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "mlp_roofline": mlp_roof,
             "spmm_roofline": spmm_roof, "cpu_baseline": cpu,
-            "phase_ms": phase, "host_issue_ms": host_issue_ms, "loss": loss_now, "lambda_rel_err_rayleigh_ritz": lam_err}
+            "samplers": samplers_info, "phase_ms": phase, "host_issue_ms": host_issue_ms, "loss": loss_now, "lambda_rel_err_rayleigh_ritz": lam_err}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -418,6 +437,7 @@ def main():
     ap.add_argument("--workload", default="icosphere1m", choices=sorted(WORKLOADS))
     ap.add_argument("--mlp-mode", default=os.environ.get("EP_MLP_MODE", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-samplers", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -40,6 +40,15 @@ class CsrMatrix:
         return cls(_to_csr_f32(A), device)
 
     @classmethod
+    def from_device_arrays(cls, rowptr, col, val, shape, symmetric=None):
+        """Wrap CSR arrays that already live on the GPU (e.g. from fem_device.assemble)."""
+        obj = cls.__new__(cls)
+        obj.shape, obj.nnz, obj.device = tuple(shape), int(col.numel()), rowptr.device
+        obj._host, obj.rowptr, obj.col, obj.val = None, rowptr, col, val
+        obj._T, obj._symmetric = None, symmetric
+        return obj
+
+    @classmethod
     def from_torch_sparse(cls, A, device):
         A = A.coalesce().cpu()
         idx = A.indices().numpy()
@@ -102,8 +111,8 @@ class OperatorPair:
         self.M = M if isinstance(M, CsrMatrix) else CsrMatrix.from_scipy(M, device)
         assert self.K.shape == self.M.shape
         self.n = self.K.shape[0]
-        self.shared = (self.K.nnz == self.M.nnz and torch.equal(self.K.rowptr, self.M.rowptr)
-                       and torch.equal(self.K.col, self.M.col))
+        self.shared = (self.K.rowptr is self.M.rowptr and self.K.col is self.M.col) or (
+            self.K.nnz == self.M.nnz and torch.equal(self.K.rowptr, self.M.rowptr) and torch.equal(self.K.col, self.M.col))
         if not self.shared:
             self._unify()
         self.symmetric = bool(assume_symmetric) if assume_symmetric is not None else (self.K.symmetric and self.M.symmetric)

@@ -245,6 +245,19 @@ EP_API int ep_voxel_select_f64_host(int64_t n_points, const double* pts_host, co
                              const int64_t* dims, int64_t* out_idx_host, int64_t max_out,
                              int64_t* out_count_host);
 
+/* ---- "next" row: sparse FEM assembly on the device (Mesh.py:180-198, :228-234, :348-364) -----------
+ * Step 1: per-triangle 3x3 stiffness / mass blocks (fp64, row-major, 9 entries per triangle) and the
+ *         linear keys row * n_verts + col of those entries.
+ * Step 2 (caller): STABLE sort of the keys, run starts / lengths of equal keys (= CSR entries).
+ * Step 3: ordered sum of every run (triangle order, like the reference loop) -> col, fp32 values for the
+ *         hot path and optionally the fp64 values. */
+EP_API int ep_fem_elements_f64(int64_t n_tris, const double* verts, const int32_t* tris, int64_t n_verts,
+                        double* k_el, double* m_el, int64_t* keys, ep_stream_t stream);
+EP_API int ep_fem_segment_sum_f64(int64_t nnz, const int64_t* seg_start, const int64_t* seg_count,
+                           const int64_t* perm, const double* k_el, const double* m_el,
+                           const int64_t* uniq_keys, int64_t n_verts, int32_t* col, float* valK, float* valM,
+                           double* valK64, double* valM64, ep_stream_t stream);
+
 /* ---- multi-GPU plumbing: halo rows --------------------------------------------------------
  * dst[r, :] = src[idx[r], :]  (pack the boundary rows of U that a peer needs). */
 EP_API int ep_gather_rows_f32(int n_idx, int k, const int32_t* idx, const float* src, int lds,

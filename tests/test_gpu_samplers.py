@@ -105,3 +105,12 @@ def test_fps_host_buffer_entry_point():
     out = np.zeros(100, dtype=np.int64)
     cabi.call("ep_fps_f64_host", 5000, pts.ctypes.data_as(ctypes.c_void_p), 100, 17, out.ctypes.data_as(ctypes.c_void_p))
     assert np.array_equal(out, samplers_port.fps_order(pts, 100, 17))
+
+
+def test_voxel_million_points_vs_oracle():
+    """BASELINE config 3 size for the voxel sampler (target 256, the reference's own probe configuration)."""
+    sampling = pkg("sampling")
+    pts = np.random.default_rng(1234).standard_normal((1_000_000, 3))
+    got = sampling.voxel_levels(pts, [256])
+    ref = samplers_port.voxel_levels(pts, [256])
+    assert np.array_equal(got[0], ref[0]) and got[0].size <= 256
