@@ -18,6 +18,7 @@ SIGNATURES = {
     "ep_version": (c_int, []),
     "ep_last_error_string": (ctypes.c_char_p, []),
     "ep_device_info": (c_int, [c_p, c_p, c_p]),
+    "ep_tune_set": (c_int, [c_int, c_int]),
     "ep_spmm_csr_f32": (c_int, [c_int, c_int, c_p, c_p, c_p, c_p, c_int, c_p, c_int, c_p]),
     "ep_spmm2_csr_f32": (c_int, [c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_int, c_p, c_p, c_int, c_p]),
     "ep_spmm2_sum_csr_f32": (c_int, [c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_p, c_int, c_f, c_p,

@@ -14,6 +14,8 @@
 
 namespace {
 
+int g_spmm_waves = 1;      // persistent grid = this many full-machine waves (tunable: ep_tune_set)
+
 template <int V> struct VecT;
 template <> struct VecT<1> { using type = float; };
 template <> struct VecT<2> { using type = float2; };
@@ -55,50 +57,52 @@ spmm_kernel(int n_rows, int kv, int lpr_shift, const int32_t* __restrict__ rowpt
             float* __restrict__ YB, int ldy) {
   using T = typename VecT<V>::type;
   const int lpr = 1 << lpr_shift;
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int row = (int)(gid >> lpr_shift);
-  const int lane = (int)(gid & (lpr - 1));
-  if (row >= n_rows) return;
-  const int start = __ldg(rowptr + row);
-  const int end = __ldg(rowptr + row + 1);
-  for (int cv = lane; cv < kv; cv += lpr) {
-    T accA = vzero<V>();
-    T accB = vzero<V>();
-    const float* xa = XA + (size_t)cv * V;
-    const float* xb = (MODE == 2) ? XB + (size_t)cv * V : nullptr;
-    for (int j = start; j < end; j += 4) {
-      int c[4];
-      float a[4], b[4];
+  const int lane = (int)(threadIdx.x & (lpr - 1));
+  const long long groups_per_grid = ((long long)gridDim.x * blockDim.x) >> lpr_shift;
+  // persistent row loop: the grid is sized to fill the machine once, every row group walks rows with a stride
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> lpr_shift; row < n_rows;
+       row += groups_per_grid) {
+    const int start = __ldg(rowptr + row);
+    const int end = __ldg(rowptr + row + 1);
+    for (int cv = lane; cv < kv; cv += lpr) {
+      T accA = vzero<V>();
+      T accB = vzero<V>();
+      const float* xa = XA + (size_t)cv * V;
+      const float* xb = (MODE == 2) ? XB + (size_t)cv * V : nullptr;
+      for (int j = start; j < end; j += 4) {
+        int c[4];
+        float a[4], b[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const bool ok = (j + u) < end;
-        c[u] = ok ? __ldg(col + j + u) : -1;
-        a[u] = ok ? __ldg(valA + j + u) : 0.f;
-        b[u] = (MODE != 0 && ok) ? __ldg(valB + j + u) : 0.f;
-      }
-      T x[4], y[4];
+        for (int u = 0; u < 4; ++u) {
+          const bool ok = (j + u) < end;
+          c[u] = ok ? __ldg(col + j + u) : -1;
+          a[u] = ok ? __ldg(valA + j + u) : 0.f;
+          b[u] = (MODE != 0 && ok) ? __ldg(valB + j + u) : 0.f;
+        }
+        T x[4], y[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        x[u] = (c[u] >= 0) ? __ldg(reinterpret_cast<const T*>(xa + (size_t)c[u] * ldx)) : vzero<V>();
-        if (MODE == 2)
-          y[u] = (c[u] >= 0) ? __ldg(reinterpret_cast<const T*>(xb + (size_t)c[u] * ldx)) : vzero<V>();
-      }
+        for (int u = 0; u < 4; ++u) {
+          x[u] = (c[u] >= 0) ? __ldg(reinterpret_cast<const T*>(xa + (size_t)c[u] * ldx)) : vzero<V>();
+          if (MODE == 2)
+            y[u] = (c[u] >= 0) ? __ldg(reinterpret_cast<const T*>(xb + (size_t)c[u] * ldx)) : vzero<V>();
+        }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (c[u] >= 0) {
-          vfma(a[u], x[u], accA);
-          if (MODE == 1) vfma(b[u], x[u], accB);
-          if (MODE == 2) vfma(b[u], y[u], accA);
+        for (int u = 0; u < 4; ++u) {
+          if (c[u] >= 0) {
+            vfma(a[u], x[u], accA);
+            if (MODE == 1) vfma(b[u], x[u], accB);
+            if (MODE == 2) vfma(b[u], y[u], accA);
+          }
         }
       }
+      if (MODE == 2) {
+        if (D != nullptr)
+          accA = vadd(accA, __ldg(reinterpret_cast<const T*>(D + (size_t)row * ldd + (size_t)cv * V)));
+        accA = vscale(accA, out_scale_dev ? __ldg(out_scale_dev) : out_scale);
+      }
+      *reinterpret_cast<T*>(YA + (size_t)row * ldy + (size_t)cv * V) = accA;
+      if (MODE == 1) *reinterpret_cast<T*>(YB + (size_t)row * ldy + (size_t)cv * V) = accB;
     }
-    if (MODE == 2) {
-      if (D != nullptr)
-        accA = vadd(accA, __ldg(reinterpret_cast<const T*>(D + (size_t)row * ldd + (size_t)cv * V)));
-      accA = vscale(accA, out_scale_dev ? __ldg(out_scale_dev) : out_scale);
-    }
-    *reinterpret_cast<T*>(YA + (size_t)row * ldy + (size_t)cv * V) = accA;
-    if (MODE == 1) *reinterpret_cast<T*>(YB + (size_t)row * ldy + (size_t)cv * V) = accB;
   }
 }
 
@@ -123,8 +127,9 @@ int launch_spmm(int n_rows, int k, const int32_t* rowptr, const int32_t* col, co
   while ((1 << lpr_shift) < kv && lpr_shift < 5) ++lpr_shift;
   const long long threads = (long long)n_rows << lpr_shift;
   const int block = 256;
-  const long long grid = (threads + block - 1) / block;
-  if (grid > 0x7fffffffLL) { ep::set_error("spmm: grid too large"); return EP_ERR_UNSUPPORTED; }
+  long long grid = (threads + block - 1) / block;
+  const long long cap = (long long)ep::sm_count() * 8 * g_spmm_waves;      // 8 CTAs of 256 threads fill one SM
+  if (grid > cap) grid = cap;
 #define EP_SPMM_LAUNCH(VV)                                                                      \
   spmm_kernel<VV, MODE><<<(unsigned)grid, block, 0, st>>>(n_rows, kv, lpr_shift, rowptr, col,   \
       valA, valB, XA, XB, ldx, D, ldd, out_scale, out_scale_dev, YA, YB, ldy)
@@ -189,6 +194,12 @@ int grid_for(long long total, int block) {
 }  // namespace
 
 extern "C" {
+
+int ep_tune_set(int key, int value) {
+  if (key == 1 && value >= 1 && value <= 64) { g_spmm_waves = value; return EP_OK; }
+  ep::set_error("ep_tune_set: unknown key or bad value");
+  return EP_ERR_INVALID;
+}
 
 int ep_spmm_csr_f32(int n_rows, int k, const int32_t* rowptr, const int32_t* col, const float* val,
                     const float* X, int ldx, float* Y, int ldy, ep_stream_t stream) {

@@ -51,6 +51,9 @@ EP_API const char* ep_last_error_string(void);
 /* sm_count, compute capability of the current device; fails (EP_ERR_CUDA) without a GPU. */
 EP_API int ep_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
+/* Tuning knobs for experiments (key 1: SpMM persistent grid = value full-machine waves, default 1). */
+EP_API int ep_tune_set(int key, int value);
+
 /* ---- sparse operators: torch.sparse.mm(K_t, U), torch.sparse.mm(M_t, U) ----------------
  * replaces multigrid_model.py:309-310 (loss), :126,:375 (normalisation), :403-404 (Rayleigh-
  * Ritz), :183-184 (features) and the autograd transposes behind :258.  The per-epoch
