@@ -51,7 +51,7 @@ EP_API const char* ep_last_error_string(void);
 /* sm_count, compute capability of the current device; fails (EP_ERR_CUDA) without a GPU. */
 EP_API int ep_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
-/* Tuning knobs for experiments (key 1: SpMM persistent grid = value full-machine waves, default 1). */
+/* Tuning knobs for experiments (key 1: SpMM persistent grid = value full-machine waves, default 4). */
 EP_API int ep_tune_set(int key, int value);
 
 /* ---- sparse operators: torch.sparse.mm(K_t, U), torch.sparse.mm(M_t, U) ----------------
