@@ -531,9 +531,10 @@ eigen_bwd_fused_sym_k32_kernel(int n, const int32_t* __restrict__ rowptr, const 
   }
   const int lane_r = lane & 7, rsub = lane >> 3;
   const int cofs = 4 * lane_r;
-  const float4 lam4 = __ldg(reinterpret_cast<const float4*>(c_lam + cofs));
-  float4 a24 = __ldg(reinterpret_cast<const float4*>(c_num + cofs));
-  a24.x *= 2.f; a24.y *= 2.f; a24.z *= 2.f; a24.w *= 2.f;
+  // coef + 1 is not 16-byte aligned: scalar loads
+  const float4 lam4 = make_float4(__ldg(c_lam + cofs), __ldg(c_lam + cofs + 1), __ldg(c_lam + cofs + 2), __ldg(c_lam + cofs + 3));
+  const float4 a24 = make_float4(2.f * __ldg(c_num + cofs), 2.f * __ldg(c_num + cofs + 1), 2.f * __ldg(c_num + cofs + 2),
+                                 2.f * __ldg(c_num + cofs + 3));
   const long long rows_per_grid = (long long)gridDim.x * 32;                  // 8 warps x 4 rows per CTA
   const long long n_iter = ((long long)n + rows_per_grid - 1) / rows_per_grid;
   for (long long it = 0; it < n_iter; ++it) {
