@@ -737,7 +737,7 @@ int ep_eigen_bwd_fused_sym_f32(int n, int k, const int32_t* rowptr, const int32_
   const long long cap = (long long)ep::sm_count() * 8;
   if (grid > cap) grid = cap;
   cudaStream_t st = ep::as_stream(stream);
-  if (k == 32) {
+  if (k == 32 && ep::tune_flag(2)) {
     long long g32 = ((long long)n + 31) / 32;
     const long long cap32 = (long long)ep::sm_count() * 8;
     if (g32 > cap32) g32 = cap32;

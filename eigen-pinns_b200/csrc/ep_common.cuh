@@ -35,6 +35,8 @@ inline int cuda_fail(cudaError_t e, const char* what) {
 inline cudaStream_t as_stream(ep_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int sm_count();   // cached
+int tune_flag(int key);          // experiment switches set through ep_tune_set (capi.cu)
+void set_tune_flag(int key, int value);
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

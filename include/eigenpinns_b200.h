@@ -51,7 +51,8 @@ EP_API const char* ep_last_error_string(void);
 /* sm_count, compute capability of the current device; fails (EP_ERR_CUDA) without a GPU. */
 EP_API int ep_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
-/* Tuning knobs for experiments (key 1: SpMM persistent grid = value full-machine waves, default 4). */
+/* Tuning knobs for experiments (key 1: SpMM persistent grid = value full-machine waves, default 4;
+ * key 2: 1 = k-32 register-resident variant of the fused backward, 0 = generic variant). */
 EP_API int ep_tune_set(int key, int value);
 
 /* ---- sparse operators: torch.sparse.mm(K_t, U), torch.sparse.mm(M_t, U) ----------------
