@@ -23,7 +23,7 @@ int sm_count() {
   return cached;
 }
 
-static int g_tune[16] = {0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+static int g_tune[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 int tune_flag(int key) { return (key >= 0 && key < 16) ? g_tune[key] : 0; }
 void set_tune_flag(int key, int value) { if (key >= 0 && key < 16) g_tune[key] = value; }
 

@@ -52,7 +52,8 @@ EP_API const char* ep_last_error_string(void);
 EP_API int ep_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* Tuning knobs for experiments (key 1: SpMM persistent grid = value full-machine waves, default 4;
- * key 2: 1 = k-32 register-resident variant of the fused backward, 0 = generic variant). */
+ * key 2: 1 = k-32 register-resident variant of the fused backward, 0 = generic variant (default; measured
+ * faster: both are instruction-issue bound, 0.29 ms vs 0.35 ms at 1 M vertices)). */
 EP_API int ep_tune_set(int key, int value);
 
 /* ---- sparse operators: torch.sparse.mm(K_t, U), torch.sparse.mm(M_t, U) ----------------
