@@ -36,8 +36,8 @@ WORKLOADS = {
 }
 HIDDEN = [256] * 6                               # reference default (src/parameters.yml)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch / vertices of tc_linear_kernel<HIDDEN> from the committed
-# ncu --set full capture (profiles/r01_v1_ncu_full_summary.csv: 0.5115 GB + 0.459 GB at 998,562 vertices)
-NCU_TRAFFIC_HIDDEN_PER_VERTEX = (0.5115e9 + 0.459e9) / 998562
+# ncu --set full capture (profiles/r01_final_ncu_full_summary.csv: 0.5122 GB + 0.4900 GB at 998,562 vertices)
+NCU_TRAFFIC_HIDDEN_PER_VERTEX = (0.5122e9 + 0.4900e9) / 998562
 
 
 def pkg(name=None):
@@ -156,7 +156,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -170,7 +170,7 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -513,7 +513,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="icosphere1m", choices=sorted(WORKLOADS))

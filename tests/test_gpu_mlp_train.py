@@ -179,4 +179,4 @@ def test_cuda_graph_replay_equals_eager(mlp_mode):
             hist.append(eng.step(e, lr=lr).cpu().numpy().copy())
         runs.append((np.array(hist), eng.params.flat.clone()))
     np.testing.assert_allclose(runs[0][0], runs[1][0], rtol=1e-4, atol=1e-9)
-    assert (runs[0][1] - runs[1][1]).abs().max().item() <= 1e-5
+    assert (runs[0][1] - runs[1][1]).abs().max().item() <= 1e-4        # a tenth of one Adam step (lr = 1e-3)
