@@ -74,76 +74,6 @@ def build_host_workload(name):
                 lam_analytic=lam_analytic)
 
 
-def build_device_torus_engine(size, k, dev, mlp_mode, rank=0, world=1):
-    """BASELINE config 5 workload built on the GPU: torus grid (size x size vertices, valence 6), FEM operators
-    from the device assembly kernels, trial subspace, node features, corrector input."""
-    import torch
-    import torch.nn as nn
-    ops, femd, sparse, engine = pkg("ops"), pkg("fem_device"), pkg("sparse"), pkg("engine")
-    if SRC not in sys.path:
-        sys.path.insert(0, SRC)
-    import corrector_model
-    n = size * size
-    i = torch.arange(size, device=dev).repeat_interleave(size)
-    j = torch.arange(size, device=dev).repeat(size)
-    u, w = 2 * np.pi * i.double() / size, 2 * np.pi * j.double() / size
-    R, r = 1.0, 0.4
-    verts = torch.stack([(R + r * torch.cos(w)) * torch.cos(u), (R + r * torch.cos(w)) * torch.sin(u), r * torch.sin(w)], 1)
-    verts = (verts - verts.mean(0)) / (verts.std(0, unbiased=False).max() + 1e-12)      # mesh_helpers.normalize_mesh
-    ip, jp = (i + 1) % size, (j + 1) % size
-    v00, v10, v11, v01 = i * size + j, ip * size + j, ip * size + jp, i * size + jp
-    tris = torch.cat([torch.stack([v00, v10, v11], 1), torch.stack([v00, v11, v01], 1)]).to(torch.int32)
-    del ip, jp, v00, v10, v11, v01
-    pair = femd.assemble(verts, tris, dev)
-    del tris
-    # adjacency for the neighbour-mean aggregation = off-diagonal pattern of K (mesh edges, both directions)
-    counts = (pair.K.rowptr[1:] - pair.K.rowptr[:-1]).long()
-    rows = torch.repeat_interleave(torch.arange(n, device=dev), counts)
-    off = pair.K.col.long() != rows
-    diag_pos = (~off).nonzero().squeeze(1)
-    adj_counts = torch.bincount(rows[off], minlength=n)
-    adj_rowptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
-    adj_rowptr[1:] = torch.cumsum(adj_counts, 0)
-    adj = sparse.CsrMatrix.from_device_arrays(adj_rowptr.to(torch.int32), pair.K.col[off].contiguous(), None, (n, n))
-    Kd, Md = pair.K.val[diag_pos].unsqueeze(1), pair.M.val[diag_pos].unsqueeze(1)
-    del rows, off, diag_pos
-    # trial subspace: lowest torus harmonics + noise, M-normalised (reference :120-130)
-    g = torch.Generator(device=dev).manual_seed(0)
-    cols = []
-    order = sorted(((a * a + 6.25 * b * b, a, b) for a in range(0, 12) for b in range(0, 6)))
-    for _, a, b in order:
-        for fu in ((torch.cos, torch.sin) if a else (torch.cos,)):
-            for fv in ((torch.cos, torch.sin) if b else (torch.cos,)):
-                if len(cols) < k:
-                    cols.append((fu(a * u) * fv(b * w)).float())
-    U0 = torch.stack(cols, 1).contiguous()
-    del cols, u, w, i, j
-    U0 += 0.05 * torch.randn(U0.shape, device=dev, generator=g)
-    U_norm = ops.m_normalize_columns(U0, pair.M)
-    del U0
-    A, B = ops.gram_pair(U_norm, pair)
-    from scipy.linalg import eigh
-    lam = torch.from_numpy(eigh(A.cpu().numpy(), B.cpu().numpy(), eigvals_only=True).astype(np.float32)).to(dev)
-    # node features of reference _compute_level_features (:159-201), single level
-    KU, MU = ops.spmm2(pair, U_norm)
-    deg = adj_counts.float().unsqueeze(1)
-    deg = deg / (deg.max() + 1e-12)
-    rmag = torch.norm(KU - MU * lam.unsqueeze(0), dim=1, keepdim=True)
-    rmag = rmag / (rmag.max() + 1e-12)
-    ray = (U_norm * KU).sum(1, keepdim=True) / ((U_norm * MU).sum(1, keepdim=True) + 1e-12)
-    ray = ray / (lam.max() + 1e-12)
-    x_feats = torch.cat([verts.float(), torch.zeros(n, 1, device=dev), deg, Kd, Md, rmag, ray, U_norm], 1).contiguous()
-    del KU, MU, rmag, ray, deg, verts
-    h = ops.neighbor_mean_concat(x_feats, adj)
-    torch.manual_seed(0)
-    model = corrector_model.SimpleCorrector(x_feats.shape[1], k, HIDDEN, 0.0).to(dev)
-    nn.init.normal_(model.net[-1].weight, mean=0.0, std=0.01)
-    nn.init.zeros_(model.net[-1].bias)
-    params = engine.FlatParams.adopt([m for m in model.net if isinstance(m, nn.Linear)])
-    eng = engine.TrainStepEngine(h, U_norm, [pair], [0], params, engine.StepConfig(), lam_target=lam, mlp_mode=mlp_mode)
-    return eng, x_feats, adj, U_norm, n, int(pair.K.nnz)
-
-
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -269,9 +199,10 @@ def run_ours(args):
     import multigrid_model
 
     kind, size, k_w = WORKLOADS[args.workload]
-    device_built = kind == "torus" and world == 1
+    device_built = kind == "torus"
     if device_built:
-        eng, x_feats, adj_dev, U_norm0, n, nnz = build_device_torus_engine(size, k_w, dev, args.mlp_mode)
+        eng, x_feats, adj_dev, U_norm0, n, nnz = pkg("workloads").build_torus_engine(
+            size, k_w, dev, args.mlp_mode, HIDDEN, rank, world)
         k, U_norm, vals_rr, edge_all = k_w, [U_norm0], None, None
         w = {"lam_analytic": None, "K": None}
     else:

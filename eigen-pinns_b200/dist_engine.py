@@ -63,10 +63,11 @@ def resolve_send_lists(plan: LevelPlan, group=None):
 
 class ShardedTrainStepEngine(TrainStepEngine):
     def __init__(self, h_local, U_base_local, plans, params: FlatParams, cfg: StepConfig, lam_target=None,
-                 mlp_mode="fp32", group=None, symmetric=True):
+                 mlp_mode="fp32", group=None, symmetric=True, pairs=None):
         dev = h_local.device
         self.plans, self.group = plans, group
-        pairs = [OperatorPair(pl.K_local, pl.M_local, dev, assume_symmetric=symmetric) for pl in plans]
+        if pairs is None:
+            pairs = [OperatorPair(pl.K_local, pl.M_local, dev, assume_symmetric=symmetric) for pl in plans]
         for pair, pl in zip(pairs, plans):
             pair.n = pl.n_own
         offsets, off = [], 0

@@ -91,7 +91,7 @@ def spmm_autograd(A, X):
 def neighbor_mean_concat(x, adj: CsrMatrix, out=None):
     """h = cat([x, mean_{j in N(i)} x_j]); reference src/corrector_model.py:23-30."""
     x = _check(_rowmajor(x))
-    n, d = x.shape
+    n, d = adj.shape[0], x.shape[1]             # adj may be a rank-local block: rows = owned vertices, columns index x
     H = out if out is not None else torch.empty((n, 2 * d), device=x.device, dtype=torch.float32)
     call("ep_neighbor_mean_concat_f32", n, d, _ptr(adj.rowptr), _ptr(adj.col), _ptr(x), x.stride(0), _ptr(H),
          H.stride(0), _stream())

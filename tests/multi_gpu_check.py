@@ -19,6 +19,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
+    if mode.startswith("torus"):
+        return torus_check(mode, rank, world, dev)
     import bench
     import config as cfg_mod
     import multigrid_model
@@ -57,6 +59,30 @@ def main():
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("MULTI_GPU_CHECK", "OK" if flag.item() == 1.0 else "FAIL", "world", world, "mode", mode,
+              "loss_single", l1[:, 5].tolist(), "loss_sharded", l2[:, 5].tolist(), "param_err", perr)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1.0 else 1)
+
+
+def torus_check(mode, rank, world, dev):
+    """Device-built torus: the sharded engine (per-rank slab assembly + grid halo plan) against the single-GPU engine."""
+    wl = importlib.import_module("eigen-pinns_b200.workloads")
+    mlp_mode = "bf16" if mode.endswith("bf16") else "fp32"
+    size, k, hidden = 192, 32, [128, 128]
+    res = []
+    for w_, r_ in ((1, 0), (world, rank)):
+        eng = wl.build_torus_engine(size, k, dev, mlp_mode, hidden, r_, w_)[0]
+        res.append((np.array([eng.step(2500 + i).cpu().numpy().copy() for i in range(4)]), eng.params.flat.clone(),
+                    eng.lams[0].clone()))
+    (l1, p1, lam1), (l2, p2, lam2) = res
+    tol = 1e-4 if mlp_mode == "fp32" else 3e-3
+    perr = (p1 - p2).abs().max().item()
+    ok = np.allclose(l1, l2, rtol=tol, atol=1e-9) and perr <= 1e-4 + (2e-3 if mlp_mode == "bf16" else 0.0)
+    ok = ok and torch.allclose(lam1, lam2, rtol=tol, atol=1e-6)
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("MULTI_GPU_CHECK", "OK" if flag.item() == 1.0 else "FAIL", "torus world", world, mlp_mode,
               "loss_single", l1[:, 5].tolist(), "loss_sharded", l2[:, 5].tolist(), "param_err", perr)
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1.0 else 1)

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("mode,launch", [("fp32", "eager"), ("bf16", "eager")])
+@pytest.mark.parametrize("mode,launch", [("fp32", "eager"), ("bf16", "eager"), ("torus_fp32", "eager"), ("torus_bf16", "eager")])
 def test_sharded_engine_matches_single_gpu(mode, launch):
     n = torch.cuda.device_count()
     if n < 2:
