@@ -389,9 +389,18 @@ def run_ours(args):
                "api": "engine.HostFedPipeline.submit/result (x_feats + U_base uploaded every step, loss read back)",
                "loss": float(e2e_loss[5])}
 
-    if rank != 0:
+    def finish():
+        """Multi-rank exit: tearing the NCCL communicator down while captured graphs still reference it can block
+        for minutes, so the ranks synchronise and leave without the orderly shutdown."""
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
     mlp_ms = phase.get("mlp_fwd", 0.0) + phase.get("mlp_bwd", 0.0)
     n_global = n
@@ -437,8 +446,7 @@ def run_ours(args):
             "spmm_roofline": spmm_roof, "cpu_baseline": cpu,
             "samplers": samplers_info, "phase_ms": phase, "host_issue_ms": host_issue_ms, "loss": loss_now, "lambda_rel_err_rayleigh_ritz": lam_err}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def main():
