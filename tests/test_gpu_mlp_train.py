@@ -184,3 +184,17 @@ def test_cuda_graph_replay_equals_eager(mlp_mode):
     # the parameter vector as a whole must agree
     diff = (runs[0][1] - runs[1][1]).norm().item() / runs[0][1].norm().item()
     assert diff <= (5e-4 if mlp_mode == "fp32" else 1e-2), diff
+
+
+def test_coarse_grid_correction_matches_reference():
+    """apply_coarse_grid_correction (reference multigrid_model.py:410-450) on the bunny / coarse pair with a regular
+    coarse operator K_c + 0.1 M_c (cond 1.6e3; the plain K_c of these meshes is singular)."""
+    import scipy.sparse as sp
+    gnn, _, fem, (K, M), (Kc, Mc) = _golden_trainer("simple")
+    g = load_golden("prep_cgc.npz")
+    P = sp.coo_matrix((g["P_data"], (g["P_row"], g["P_col"])), shape=(K.shape[0], Kc.shape[0]))
+    K_reg = sp.coo_matrix(Kc + 0.1 * Mc)
+    U_cgc, lam = gnn.apply_coarse_grid_correction(torch.from_numpy(g["U1"]).float(), K, M, K_reg, P)
+    np.testing.assert_allclose(lam.cpu().numpy(), g["lam_f"], rtol=2e-4, atol=2e-5)
+    ref = g["U_cgc"]
+    assert np.abs(U_cgc.cpu().numpy() - ref).max() <= 2e-3 * np.abs(ref).max()
