@@ -179,6 +179,51 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ our arm
+def build_engine(args, dev, rank, world):
+    """Set-up (untimed): workload -> training-step engine.  Triangle meshes built on the host go through the
+    reference-shaped API (MultigridGNN._normalize_eigenvectors / _build_features / _initialize_model / _make_engine);
+    the torus grids are generated, assembled and sharded on the device (eigen-pinns_b200/workloads.py)."""
+    import torch
+    kind, size, k = WORKLOADS[args.workload]
+    if kind == "torus":
+        eng, x_feats, adj, U_norm, n, nnz = pkg("workloads").build_torus_engine(size, k, dev, args.mlp_mode, HIDDEN,
+                                                                               rank, world)
+        return dict(engine=eng, n=n, k=k, nnz=nnz, lam_err=None, x_feats=x_feats, U_norm=U_norm, edge_index=None,
+                    adjacency=adj)
+    if SRC not in sys.path:
+        sys.path.insert(0, SRC)
+    import config as cfg_mod
+    import multigrid_model
+    w = build_host_workload(args.workload)
+    n = w["verts"].shape[0]
+    cfg = cfg_mod.PINNConfig.from_yaml(os.path.join(SRC, "parameters.yml"))
+    cfg.n_modes, cfg.mlp_mode, cfg.seed, cfg.hidden_layers = k, args.mlp_mode, 0, HIDDEN
+    stdout, sys.stdout = sys.stdout, open(os.devnull, "w")      # the drop-in modules print like the reference
+    try:
+        gnn = multigrid_model.MultigridGNN(cfg)
+        edges = torch.from_numpy(w["edges"])
+        U_norm = gnn._normalize_eigenvectors([w["U0"]], [w["M"]])
+        vals_rr, _ = gnn.refine_eigenvectors(w["modes"].astype(np.float32), w["K"], w["M"])
+        lam0 = torch.from_numpy(vals_rr.astype(np.float32))
+        x_feats, edge_all, A_norm = gnn._build_features([w["verts"]], U_norm, [lam0], [edges], [w["K"]], [w["M"]])
+        gnn._initialize_model(x_feats.shape[1], k, HIDDEN, 0.0)
+        opt, _ = gnn._create_optimizer(gnn.lr, gnn.weight_decay)
+        if world > 1:
+            eng = pkg("dist_engine").make_sharded_engine(gnn, x_feats, edge_all, U_norm[0], w["K"], w["M"], lam0, opt,
+                                                         rank, world)
+        else:
+            eng = gnn._make_engine(x_feats, edge_all, A_norm, U_norm[0], [w["K"]], [w["M"]], lam0, [0], opt)
+    finally:
+        sys.stdout = stdout
+    lam_err = None
+    if w["lam_analytic"] is not None:             # Rayleigh-Ritz of the analytic harmonics vs l(l+1)/(2 rho^2)
+        ref = w["lam_analytic"]
+        nz = ref > 0
+        lam_err = float(np.max(np.abs(np.sort(vals_rr)[nz] - ref[nz]) / ref[nz]))
+    return dict(engine=eng, n=n, k=k, nnz=int(w["K"].nnz), lam_err=lam_err, x_feats=x_feats, U_norm=U_norm[0],
+                edge_index=edge_all, adjacency=None)
+
+
 def run_ours(args):
     import torch
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -193,53 +238,12 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     pkg().require_library()
     cabi = pkg("_cabi")
-    if SRC not in sys.path:
-        sys.path.insert(0, SRC)
-    import config as cfg_mod
-    import multigrid_model
-
-    kind, size, k_w = WORKLOADS[args.workload]
-    device_built = kind == "torus"
-    if device_built:
-        eng, x_feats, adj_dev, U_norm0, n, nnz = pkg("workloads").build_torus_engine(
-            size, k_w, dev, args.mlp_mode, HIDDEN, rank, world)
-        k, U_norm, vals_rr, edge_all = k_w, [U_norm0], None, None
-        w = {"lam_analytic": None, "K": None}
-    else:
-        w = build_host_workload(args.workload)
-        n, k = w["verts"].shape[0], w["k"]
-    cfg = cfg_mod.PINNConfig.from_yaml(os.path.join(SRC, "parameters.yml"))
-    cfg.n_modes, cfg.mlp_mode, cfg.seed, cfg.hidden_layers = k, args.mlp_mode, 0, HIDDEN
-    devnull = open(os.devnull, "w")
-    stdout, sys.stdout = sys.stdout, devnull                 # the drop-in modules print like the reference
-    try:
-        if device_built:
-            raise StopIteration
-        gnn = multigrid_model.MultigridGNN(cfg)
-        edges = torch.from_numpy(w["edges"])
-        U_norm = gnn._normalize_eigenvectors([w["U0"]], [w["M"]])
-        vals_rr, _ = gnn.refine_eigenvectors(w["modes"].astype(np.float32), w["K"], w["M"])
-        lam0 = torch.from_numpy(vals_rr.astype(np.float32))
-        x_feats, edge_all, A_norm = gnn._build_features([w["verts"]], U_norm, [lam0], [edges], [w["K"]], [w["M"]])
-        gnn._initialize_model(x_feats.shape[1], k, HIDDEN, 0.0)
-        opt, sched = gnn._create_optimizer(gnn.lr, gnn.weight_decay)
-        if world > 1:
-            dist_engine = pkg("dist_engine")
-            eng = dist_engine.make_sharded_engine(gnn, x_feats, edge_all, U_norm[0], w["K"], w["M"], lam0, opt, rank, world)
-        else:
-            eng = gnn._make_engine(x_feats, edge_all, A_norm, U_norm[0], [w["K"]], [w["M"]], lam0, [0], opt)
-    except StopIteration:
-        pass
-    finally:
-        sys.stdout = stdout
-    lam_err = None
-    if w["lam_analytic"] is not None:
-        ref = w["lam_analytic"]
-        nz = ref > 0
-        lam_err = float(np.max(np.abs(np.sort(vals_rr)[nz] - ref[nz]) / ref[nz]))
+    wl = build_engine(args, dev, rank, world)
+    eng, n, k, nnz, lam_err = wl["engine"], wl["n"], wl["k"], wl["nnz"], wl["lam_err"]
+    x_feats, U_norm, edge_all, adj_dev = wl["x_feats"], [wl["U_norm"]], wl["edge_index"], wl["adjacency"]
+    device_built = adj_dev is not None
     d_in = eng.h.shape[1]
     flops_v = mlp_flops_per_vertex(d_in, HIDDEN, k)
-    nnz = nnz if device_built else w["K"].nnz
     epoch0 = 2500                                            # mid-ramp: correction scale 5.0, non-zero gradients
 
     def barrier():
