@@ -164,7 +164,9 @@ def run_reference(args):
     kind, size, k = WORKLOADS[args.workload]
     full_n = 10 * size * size + 2 if kind == "icosphere" else size * size
     sample = "icosphere100k" if kind == "icosphere" else "torus1m"
-    r = cpu_reference_steps_per_s(sample, full_n, max(1, min(args.steps, 3)), max(1, min(args.warmup, 1)))
+    # torchrun pins OMP_NUM_THREADS=1; the reference arm is entitled to every host core
+    r = cpu_reference_steps_per_s(sample, full_n, max(1, min(args.steps, 3)), max(1, min(args.warmup, 1)),
+                                  threads=os.cpu_count())
     sample_txt = ("oracle/step_port.py (torch-CPU port of the reference step) on %s = %d vertices, %.0f ms/step, "
                   "scaled x%.2f to %d vertices" % (sample, r["sample_vertices"], r["sample_ms"],
                                                   full_n / r["sample_vertices"], full_n))
@@ -434,7 +436,7 @@ def run_ours(args):
         sample = "icosphere100k" if kind == "icosphere" else "torus1m"
         if n_global < 150000:
             sample = args.workload
-        r = cpu_reference_steps_per_s(sample, n_global, 2, 1)
+        r = cpu_reference_steps_per_s(sample, n_global, 2, 1, threads=os.cpu_count())
         cpu = {"value": r["steps_per_s"], "unit": "steps/s", "cores": r["threads"], "kind": "port",
                "sample": "oracle/step_port.py on %s (%d vertices, %.0f ms/step) scaled to %d vertices"
                          % (sample, r["sample_vertices"], r["sample_ms"], n_global)}
