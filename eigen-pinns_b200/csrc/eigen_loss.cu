@@ -1,9 +1,11 @@
 // Eigen-loss kernels: Rayleigh quotient, residual, Gram / orthonormality (forward partials,
 // finalisation, analytic backward).  Reference arithmetic: src/multigrid_model.py:291-348.
 //
-// Data layout: U, KU, MU are row-major n x k fp32 in HBM.  Everything that is summed over
-// vertices is accumulated in fp32 for at most one 32-row tile and then folded into fp64, so the
-// one-pass residual expansion sum(KU^2) - 2 lam sum(KU MU) + lam^2 sum(MU^2) does not cancel.
+// Data layout: U, KU, MU are row-major n x k fp32 in HBM.  The four column sums behind the Rayleigh
+// quotient and the one-pass residual expansion sum(KU^2) - 2 lam sum(KU MU) + lam^2 sum(MU^2) are
+// accumulated in fp64 from the first product on (exact products, ~1e-16 relative sums), so the
+// expansion stays accurate near convergence where the residual is a tiny difference of large terms.
+// The Gram matrix is accumulated in fp32 for at most four 32-row tiles and then folded into fp64.
 // Algorithmic traffic of the partials kernel: 12 n k bytes read, flops 2 n k^2 + 8 n k.
 #include "ep_common.cuh"
 
@@ -135,16 +137,19 @@ eigen_partials_kernel(int n, int k, const float* __restrict__ U, int ldu, const 
     for (int cc = 0; cc < CPL; ++cc) {
       const int c = lane + 32 * cc;
       if (c < KP) {
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        // fp64 from the first product on: products of two fp32 values are exact in fp64, so the one-pass
+        // expansion sKK - 2 lam sKM + lam^2 sMM keeps ~9 digits even when the residual is 1e-4 of |KU|
+        // (near convergence); B200 issues DFMA at half the FFMA rate and this loop is 4 DFMA per 12 bytes.
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
         for (int r = warp; r < R; r += kPartialThreads / 32) {
-          const float u = Us[r][c], ku = KUs[r][c], mu = MUs[r][c];
-          s0 = fmaf(u, ku, s0);
-          s1 = fmaf(ku, ku, s1);
-          s2 = fmaf(ku, mu, s2);
-          s3 = fmaf(mu, mu, s3);
+          const double u = (double)Us[r][c], ku = (double)KUs[r][c], mu = (double)MUs[r][c];
+          s0 = fma(u, ku, s0);
+          s1 = fma(ku, ku, s1);
+          s2 = fma(ku, mu, s2);
+          s3 = fma(mu, mu, s3);
         }
-        c64[0][cc] += (double)s0; c64[1][cc] += (double)s1;
-        c64[2][cc] += (double)s2; c64[3][cc] += (double)s3;
+        c64[0][cc] += s0; c64[1][cc] += s1;
+        c64[2][cc] += s2; c64[3][cc] += s3;
       }
     }
   }
@@ -222,12 +227,13 @@ __device__ double block_sum_256(double v, double* scratch) {
 
 __global__ void __launch_bounds__(256)
 eigen_finalize_kernel(int k, double n_global, const double* __restrict__ P, float w_res, float w_orth,
-                      int level0, const float* __restrict__ lam_target, float w_trace, float w_order,
+                      int flags, const float* __restrict__ lam_target, float w_trace, float w_order,
                       float w_eigen, const float* __restrict__ lam_bar_extra, float* __restrict__ lam_out,
                       float* __restrict__ coef, double* __restrict__ loss_acc) {
   __shared__ double s_lam[128];
   __shared__ double scratch[8];
   const int tid = threadIdx.x;
+  const bool level0 = (flags & EP_FINALIZE_EIGENVALUE_TERMS) != 0;
   const double* G = P;
   const double* num = P + (size_t)k * k;
   const double* sKK = num + k;
@@ -299,8 +305,13 @@ eigen_finalize_kernel(int k, double n_global, const double* __restrict__ P, floa
     coef[0] = (float)c_res;
     const double t0 = (double)w_res * L_res, t1 = (double)w_orth * L_orth;
     const double t2 = (double)w_trace * tr_sum, t3 = (double)w_order * ord_sum, t4 = (double)w_eigen * eig_sum;
-    loss_acc[0] += t0; loss_acc[1] += t1; loss_acc[2] += t2; loss_acc[3] += t3; loss_acc[4] += t4;
-    loss_acc[5] += t0 + t1 + t2 + t3 + t4;
+    if (flags & EP_FINALIZE_OVERWRITE) {      // first level of a step: no separate zero-fill launch
+      loss_acc[0] = t0; loss_acc[1] = t1; loss_acc[2] = t2; loss_acc[3] = t3; loss_acc[4] = t4;
+      loss_acc[5] = t0 + t1 + t2 + t3 + t4;
+    } else {
+      loss_acc[0] += t0; loss_acc[1] += t1; loss_acc[2] += t2; loss_acc[3] += t3; loss_acc[4] += t4;
+      loss_acc[5] += t0 + t1 + t2 + t3 + t4;
+    }
   }
 }
 
@@ -685,13 +696,13 @@ int ep_eigen_partials_f32(int n, int k, const float* U, int ldu, const float* KU
 }
 
 int ep_eigen_finalize_f32(int k, double n_global, const double* partials, float w_res, float w_orth,
-                          int level0, const float* lam_target, float w_trace, float w_order, float w_eigen,
+                          int flags, const float* lam_target, float w_trace, float w_order, float w_eigen,
                           const float* lam_bar_extra, float* lam_out, float* coef, double* loss_acc,
                           ep_stream_t stream) {
   EP_REQUIRE(k > 0 && k <= 128, "k out of range");
   EP_REQUIRE(n_global > 0, "n_global must be positive");
   EP_REQUIRE(partials && coef && loss_acc, "null pointer");
-  eigen_finalize_kernel<<<1, 256, 0, ep::as_stream(stream)>>>(k, n_global, partials, w_res, w_orth, level0,
+  eigen_finalize_kernel<<<1, 256, 0, ep::as_stream(stream)>>>(k, n_global, partials, w_res, w_orth, flags,
                                                                lam_target, w_trace, w_order, w_eigen,
                                                                lam_bar_extra, lam_out, coef, loss_acc);
   EP_LAUNCH_CHECK("eigen_finalize_kernel");

@@ -315,6 +315,273 @@ __global__ void __launch_bounds__(LINEAR_THREADS, 1) tc_linear_kernel(LinearArgs
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
+// ------------------------------------------------------------------------------------------- layer chain
+// tc_chain_kernel: ALL layers of the corrector MLP for a pair of 128-vertex tiles in one persistent CTA.
+//   MODE_CHAIN_FWD  x0 -> relu(. W0^T + b0) -> ... -> . W_{L-1}^T + b_{L-1}   (corrector_model.py:31)
+//   MODE_CHAIN_DX   dZ_{L-1} -> (. W_{L-1}) * mask_{L-2} -> ... -> dZ_0        (autograd of :258)
+// The activation tile never leaves the SM between layers: the epilogue of layer l writes bf16 straight into the
+// shared-memory slot that is the A operand of layer l+1 (same packed K-major layout, in place) and, because the
+// backward pass needs it, streams the same 16-byte chunks to HBM (write-only traffic; nothing is read back).
+// Weights do not fit one SM (0.72 MB for 82->256x6->32), so they stream from L2 through a ring of 16 KB K-slabs;
+// two tiles advance in lock step so that every slab feeds two MMAs (M = 256 per weight pass halves the L2 traffic).
+// TMEM: tile 0 accumulates in columns [0, 256), tile 1 in [256, 512).
+// Warp roles: warp 0 = weight-slab TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue
+// (tile = (warp - 2) / 4, TMEM lane quadrant = warp % 4); the first epilogue thread also issues the input-tile
+// TMA of the next pair as soon as the last layer's MMAs have retired.
+// Algorithmic HBM bytes per vertex (forward, 82->256x6->32): read 2*96, write 6*(2*256 + 32) + 2*4*32 -> 3.7 KB,
+// against 6.9 KB for the layer-by-layer kernels (every hidden activation was read back once).
+constexpr int CH_MAX_LAYERS = 8;
+constexpr int CH_THREADS = 320;
+constexpr int CH_STAGES = 5;
+constexpr int CH_SLAB_BYTES = 16384;          // K = 32 rows of a 256-wide weight matrix
+constexpr int CH_ACT_BYTES = 65536;           // one 128 x 256 bf16 tile
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+struct ChainLayer {
+  const uint8_t* B;        // packed weights [KC][N][8] bf16 (W for the forward chain, W^T for the dX chain)
+  const float* bias;       // forward: bias[0..n_bias) or NULL
+  uint8_t* out_packed;     // [tile][N/8][128][8] or NULL (not stored)
+  uint32_t* mask;          // forward: ReLU bit mask written (may be NULL); dX: ReLU bit mask read
+  int KC, N, n_bias, pad_;
+};
+struct ChainArgs {
+  const uint8_t* A0;       // packed input tiles, L[0].KC chunks each
+  int n_tiles, n_layers;
+  ChainLayer L[CH_MAX_LAYERS];
+  float* corr; int ldc;    // forward, last layer: fp32 rows (corr may be NULL)
+  const float* U_base; float* U_pred; int ldu; float scale; const float* scale_dev;
+  int n_rows, n_out, relu;
+};
+enum ChainMode { MODE_CHAIN_FWD = 0, MODE_CHAIN_DX = 1 };
+
+template <int MODE>
+__global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_kernel(const __grid_constant__ ChainArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* act0 = smem;
+  uint8_t* act1 = smem + CH_ACT_BYTES;
+  uint8_t* ring = smem + 2 * CH_ACT_BYTES;
+  float* bias_s = reinterpret_cast<float*>(ring + CH_STAGES * CH_SLAB_BYTES);          // [CH_MAX_LAYERS][256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + CH_MAX_LAYERS * 256);
+  uint64_t* wfull = bars;                     // [CH_STAGES]
+  uint64_t* wempty = bars + CH_STAGES;        // [CH_STAGES]
+  uint64_t* in_full = wempty + CH_STAGES;     // input tiles of a pair have landed
+  uint64_t* acc_full = in_full + 1;           // all MMAs of one layer (both tiles) have retired
+  uint64_t* act_ready = acc_full + 1;         // 256 epilogue threads: next operand written, accumulators drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(act_ready + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = a.n_layers;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < CH_STAGES; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
+    mbar_init(in_full, 1);
+    mbar_init(acc_full, 1);
+    mbar_init(act_ready, 256);
+    fence_barrier_init();
+  }
+  if (MODE == MODE_CHAIN_FWD) {
+    for (int i = threadIdx.x; i < L * 256; i += blockDim.x) {
+      const int l = i >> 8, c = i & 255;
+      bias_s[i] = (a.L[l].bias && c < a.L[l].n_bias) ? a.L[l].bias[c] : 0.f;
+    }
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_pairs = (a.n_tiles + 1) >> 1;
+  const uint32_t in_bytes = (uint32_t)a.L[0].KC * CHUNK_BYTES;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        for (int l = 0; l < L; ++l) {
+          const uint32_t slab_bytes = (uint32_t)a.L[l].N * 64u;
+          const int n_slabs = a.L[l].KC >> 2;
+          const uint8_t* src = a.L[l].B;
+          for (int s = 0; s < n_slabs; ++s) {
+            mbar_wait(&wempty[stage], phase ^ 1);
+            mbar_expect_tx(&wfull[stage], slab_bytes);
+            bulk_g2s(ring + stage * CH_SLAB_BYTES, src + (size_t)s * slab_bytes, slab_bytes, &wfull[stage]);
+            if (++stage == CH_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      uint32_t g = 0, pi = 0;
+      const uint32_t a0 = smem_u32(act0), a1 = smem_u32(act1);
+      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pi) {
+        const bool two = (2 * pair + 1) < a.n_tiles;
+        for (int l = 0; l < L; ++l, ++g) {
+          if (l == 0) mbar_wait(in_full, pi & 1);
+          if (g > 0) mbar_wait(act_ready, (g - 1) & 1);
+          tc_fence_after();
+          const int N = a.L[l].N;
+          const uint32_t idesc = make_idesc(TILE_M, N, false, false);
+          const uint32_t b_lbo = (uint32_t)N * 16;
+          const int n_slabs = a.L[l].KC >> 2;
+          for (int s = 0; s < n_slabs; ++s) {
+            mbar_wait(&wfull[stage], phase);
+            tc_fence_after();
+            const uint32_t b_base = smem_u32(ring + stage * CH_SLAB_BYTES);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint64_t bdesc = make_desc(b_base + (uint32_t)(j * 2) * b_lbo, b_lbo, 128);
+              const uint32_t a_off = (uint32_t)(s * 4 + j * 2) * CHUNK_BYTES;
+              const uint32_t accum = (s | j) != 0 ? 1u : 0u;
+              umma_bf16(tmem_base, make_desc(a0 + a_off, CHUNK_BYTES, 128), bdesc, idesc, accum);
+              if (two) umma_bf16(tmem_base + 256u, make_desc(a1 + a_off, CHUNK_BYTES, 128), bdesc, idesc, accum);
+            }
+            umma_commit(&wempty[stage]);
+            if (++stage == CH_STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(acc_full);
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int t = (warp - 2) >> 2;                   // which tile of the pair
+    const int r = q * 32 + lane;
+    uint8_t* act = t ? act1 : act0;
+    const bool elected = (warp == 2 && lane == 0);
+    auto issue_input = [&](int pair) {
+      const int t0 = 2 * pair;
+      const bool two = (t0 + 1) < a.n_tiles;
+      mbar_expect_tx(in_full, two ? 2 * in_bytes : in_bytes);
+      bulk_g2s(act0, a.A0 + (size_t)t0 * in_bytes, in_bytes, in_full);
+      if (two) bulk_g2s(act1, a.A0 + (size_t)(t0 + 1) * in_bytes, in_bytes, in_full);
+    };
+    if (elected && (int)blockIdx.x < n_pairs) issue_input(blockIdx.x);
+    const float scale = (MODE == MODE_CHAIN_FWD && a.scale_dev) ? *a.scale_dev : a.scale;
+    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
+    uint32_t g = 0;
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const int tile = 2 * pair + t;
+      const bool valid = tile < a.n_tiles;            // warp-uniform
+      const long long row = (long long)tile * TILE_M + r;
+      for (int l = 0; l < L; ++l, ++g) {
+        const ChainLayer& Ly = a.L[l];
+        const int N = Ly.N, ncb = N >> 5;
+        const bool last = (l == L - 1);
+        uint32_t mw[8];
+        if (MODE == MODE_CHAIN_DX) {
+#pragma unroll
+          for (int w = 0; w < 8; ++w) mw[w] = (valid && w < ncb) ? __ldg(Ly.mask + (size_t)row * ncb + w) : 0u;
+        }
+        mbar_wait(acc_full, g & 1);
+        tc_fence_after();
+        if (last && elected) {                         // operand buffers are free: fetch the next pair's input now
+          const int next = pair + (int)gridDim.x;
+          if (next < n_pairs) issue_input(next);
+        }
+        if (valid) {
+          if (MODE == MODE_CHAIN_FWD && last) {
+            // fp32 rows: every thread owns one vertex row and writes whole 128-byte lines of it
+            const bool in_rows = row < a.n_rows;
+            const bool vec = ((a.ldc | a.ldu | a.n_out) & 3) == 0 &&
+                             ((reinterpret_cast<uintptr_t>(a.corr) | reinterpret_cast<uintptr_t>(a.U_base) |
+                               reinterpret_cast<uintptr_t>(a.U_pred)) & 15u) == 0;
+            const float* bl = bias_s + l * 256;
+            for (int cb = 0; cb < ncb; ++cb) {
+              float4 ub[8];
+              if (vec && in_rows && a.U_pred) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const int col = cb * 32 + 4 * j;
+                  ub[j] = col < a.n_out ? __ldg(reinterpret_cast<const float4*>(a.U_base + (size_t)row * a.ldu + col))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+              }
+              uint32_t v[32];
+              tmem_ld32(t_addr + cb * 32, v);
+              if (in_rows) {
+                if (vec) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const int col = cb * 32 + 4 * j;
+                    if (col < a.n_out) {
+                      float4 c;
+                      c.x = __uint_as_float(v[4 * j]) + bl[col];         c.y = __uint_as_float(v[4 * j + 1]) + bl[col + 1];
+                      c.z = __uint_as_float(v[4 * j + 2]) + bl[col + 2]; c.w = __uint_as_float(v[4 * j + 3]) + bl[col + 3];
+                      if (a.corr) *reinterpret_cast<float4*>(a.corr + (size_t)row * a.ldc + col) = c;
+                      if (a.U_pred) {
+                        float4 u;
+                        u.x = __fadd_rn(ub[j].x, __fmul_rn(scale, c.x)); u.y = __fadd_rn(ub[j].y, __fmul_rn(scale, c.y));
+                        u.z = __fadd_rn(ub[j].z, __fmul_rn(scale, c.z)); u.w = __fadd_rn(ub[j].w, __fmul_rn(scale, c.w));
+                        *reinterpret_cast<float4*>(a.U_pred + (size_t)row * a.ldu + col) = u;
+                      }
+                    }
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) {
+                    const int col = cb * 32 + j;
+                    if (col < a.n_out) {
+                      const float c = __uint_as_float(v[j]) + bl[col];
+                      if (a.corr) a.corr[(size_t)row * a.ldc + col] = c;
+                      if (a.U_pred)
+                        a.U_pred[(size_t)row * a.ldu + col] =
+                            __fadd_rn(__ldg(a.U_base + (size_t)row * a.ldu + col), __fmul_rn(scale, c));
+                    }
+                  }
+                }
+              }
+            }
+          } else {
+            const size_t tile_off = (size_t)tile * (N >> 3) * CHUNK_BYTES + (size_t)r * 16;
+            const float* bl = bias_s + l * 256;
+            const bool to_smem = !last;
+#pragma unroll
+            for (int cb = 0; cb < 8; ++cb) {
+              if (cb < ncb) {
+                uint32_t v[32];
+                tmem_ld32(t_addr + cb * 32, v);
+                uint32_t bits = 0;
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {
+                  const int c = cb * 4 + g4;
+                  float f[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g4 * 8 + j]);
+                  if (MODE == MODE_CHAIN_FWD) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      f[j] += bl[c * 8 + j];
+                      if (a.relu) f[j] = fmaxf(f[j], 0.f);
+                      bits |= (f[j] > 0.f ? 1u : 0u) << (g4 * 8 + j);
+                    }
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] = ((mw[cb] >> (g4 * 8 + j)) & 1u) ? f[j] : 0.f;
+                  }
+                  uint4 o;
+                  o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+                  o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+                  if (to_smem) *reinterpret_cast<uint4*>(act + (size_t)c * CHUNK_BYTES + (size_t)r * 16) = o;
+                  if (Ly.out_packed) *reinterpret_cast<uint4*>(Ly.out_packed + tile_off + (size_t)c * CHUNK_BYTES) = o;
+                }
+                if (MODE == MODE_CHAIN_FWD && Ly.mask) Ly.mask[(size_t)row * ncb + cb] = bits;
+              }
+            }
+          }
+        }
+        if (!last) fence_proxy_async_smem();           // generic-proxy writes -> visible to the MMA (async proxy)
+        tc_fence_before();
+        mbar_arrive(act_ready);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
 // ------------------------------------------------------------------------------------------- dW
 constexpr int DW_THREADS = 192;
 constexpr int DW_XSTAGES = 3;          // half tiles of X: 16 chunks = 32 KB
@@ -606,6 +873,36 @@ int launch_linear(const LinearArgs& a, cudaStream_t st, int max_ctas = 0) {
 
 bool dims_ok(int kp, int np) { return kp % 32 == 0 && np % 32 == 0 && kp >= 32 && np >= 32 && kp <= 256 && np <= 256; }
 
+template <int MODE>
+int launch_chain(const ChainArgs& a, cudaStream_t st) {
+  const size_t smem = 2 * (size_t)CH_ACT_BYTES + (size_t)CH_STAGES * CH_SLAB_BYTES + sizeof(float) * CH_MAX_LAYERS * 256 +
+                      8 * (2 * CH_STAGES + 3) + 16 + 128;
+  static bool configured = false;
+  if (!configured) {
+    EP_CUDA_CHECK(cudaFuncSetAttribute(tc_chain_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int n_pairs = (a.n_tiles + 1) / 2;
+  int grid = ep::sm_count();
+  if (grid > n_pairs) grid = n_pairs;
+  tc_chain_kernel<MODE><<<grid, CH_THREADS, smem, st>>>(a);
+  EP_LAUNCH_CHECK("tc_chain_kernel");
+  return EP_OK;
+}
+
+int chain_dims_ok(const char* who, int n_layers, const int* dims_padded) {
+  if (n_layers < 1 || n_layers > CH_MAX_LAYERS || !dims_padded) {
+    ep::set_error("%s: 1 <= n_layers <= %d", who, CH_MAX_LAYERS);
+    return EP_ERR_UNSUPPORTED;
+  }
+  for (int l = 0; l <= n_layers; ++l)
+    if (dims_padded[l] % 32 != 0 || dims_padded[l] < 32 || dims_padded[l] > 256) {
+      ep::set_error("%s: padded widths must be multiples of 32 in [32, 256]", who);
+      return EP_ERR_UNSUPPORTED;
+    }
+  return EP_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -683,6 +980,53 @@ int ep_tc_linear_dx_bf16(int n, int out_padded, int in_padded, const void* dZ_pa
   a.out_packed = static_cast<uint8_t*>(dZprev_packed); a.mask_in = static_cast<const uint32_t*>(relu_mask);
   a.n_rows = n; a.n_out = in_padded;
   return launch_linear<MODE_DX>(a, ep::as_stream(stream), max_ctas);
+}
+
+int ep_tc_chain_fwd_bf16(int n, int n_layers, const int* dims_padded, const int* dims_out, const void* A0_packed,
+                         const void* const* Wp, const float* const* bias, void* const* act_out,
+                         void* const* relu_mask_out, float* corr, int ldc, const float* U_base, float scale,
+                         const float* scale_dev, float* U_pred, int ldu, ep_stream_t stream) {
+  EP_REQUIRE(n > 0 && A0_packed && Wp && bias && dims_out, "bad argument");
+  EP_REQUIRE(n_layers >= 2, "the forward chain needs at least one hidden layer");
+  if (int rc = chain_dims_ok("ep_tc_chain_fwd_bf16", n_layers, dims_padded)) return rc;
+  const int k = dims_out[n_layers - 1];
+  EP_REQUIRE(k > 0 && k <= dims_padded[n_layers], "bad output width");
+  EP_REQUIRE((U_base == nullptr) == (U_pred == nullptr) && (!U_pred || ldu >= k) && (!corr || ldc >= k),
+             "U_base / U_pred / corr mismatch");
+  EP_REQUIRE(corr || U_pred, "nothing to write");
+  ChainArgs a{};
+  a.A0 = static_cast<const uint8_t*>(A0_packed);
+  a.n_tiles = n_tiles_for(n); a.n_layers = n_layers;
+  for (int l = 0; l < n_layers; ++l) {
+    EP_REQUIRE(Wp[l], "null weight pointer");
+    a.L[l].B = static_cast<const uint8_t*>(Wp[l]);
+    a.L[l].bias = bias[l];
+    a.L[l].KC = dims_padded[l] / 8; a.L[l].N = dims_padded[l + 1]; a.L[l].n_bias = dims_out[l];
+    const bool hidden = l + 1 < n_layers;
+    a.L[l].out_packed = (hidden && act_out) ? static_cast<uint8_t*>(act_out[l]) : nullptr;
+    a.L[l].mask = (hidden && relu_mask_out) ? static_cast<uint32_t*>(relu_mask_out[l]) : nullptr;
+  }
+  a.corr = corr; a.ldc = ldc; a.U_base = U_base; a.U_pred = U_pred; a.ldu = ldu; a.scale = scale; a.scale_dev = scale_dev;
+  a.n_rows = n; a.n_out = k; a.relu = 1;
+  return launch_chain<MODE_CHAIN_FWD>(a, ep::as_stream(stream));
+}
+
+int ep_tc_chain_dx_bf16(int n, int n_layers, const int* dims_padded, const void* dZ_packed, const void* const* WTp,
+                        const void* const* relu_mask, void* const* dZ_out, ep_stream_t stream) {
+  EP_REQUIRE(n > 0 && dZ_packed && WTp && relu_mask && dZ_out, "bad argument");
+  if (int rc = chain_dims_ok("ep_tc_chain_dx_bf16", n_layers, dims_padded)) return rc;
+  ChainArgs a{};
+  a.A0 = static_cast<const uint8_t*>(dZ_packed);
+  a.n_tiles = n_tiles_for(n); a.n_layers = n_layers;
+  for (int l = 0; l < n_layers; ++l) {
+    EP_REQUIRE(WTp[l] && relu_mask[l] && dZ_out[l], "null pointer in a layer table");
+    a.L[l].B = static_cast<const uint8_t*>(WTp[l]);
+    a.L[l].KC = dims_padded[l] / 8; a.L[l].N = dims_padded[l + 1];
+    a.L[l].out_packed = static_cast<uint8_t*>(dZ_out[l]);
+    a.L[l].mask = const_cast<uint32_t*>(static_cast<const uint32_t*>(relu_mask[l]));
+  }
+  a.n_rows = n;
+  return launch_chain<MODE_CHAIN_DX>(a, ep::as_stream(stream));
 }
 
 size_t ep_tc_dw_workspace_bytes(void) { return sizeof(float) * (size_t)ep::sm_count() * (256 * 256 + 256); }

@@ -39,18 +39,19 @@ __global__ void sqnorm_final_kernel(int n_parts, double* __restrict__ out) {
 __global__ void __launch_bounds__(256)
 adam_clip_kernel(size_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                  float* __restrict__ v, float lr, const float* __restrict__ hyper_dev, float beta1, float beta2,
-                 float eps, float wd, double bc1_v, double bc2_sqrt_v, float max_norm,
-                 const double* __restrict__ sq_norm) {
+                 float eps, float wd, int step_v, float max_norm, const double* __restrict__ sq_norm) {
   float coef = 1.0f;
   if (sq_norm != nullptr && max_norm > 0.f) {
     const float total = (float)sqrt(*sq_norm);
     coef = fminf(max_norm / (total + 1e-6f), 1.0f);
   }
-  // hyper_dev = {lr, 1 - beta1^t, sqrt(1 - beta2^t)} in device memory (CUDA-graph replay), else by value
+  // hyper_dev = {float lr, int32 step} in device memory (CUDA-graph replay), else by value.  The bias corrections
+  // are evaluated HERE, in double, from the integer step in both cases: replay and eager launches agree bit for bit.
   const float lr_now = hyper_dev ? hyper_dev[0] : lr;
-  const double bc1 = hyper_dev ? (double)hyper_dev[1] : bc1_v;
+  const int t = hyper_dev ? __float_as_int(hyper_dev[1]) : step_v;
+  const double bc1 = 1.0 - pow((double)beta1, (double)t);
   const float step_size = (float)((double)lr_now / bc1);
-  const float bc2s = hyper_dev ? hyper_dev[2] : (float)bc2_sqrt_v;
+  const float bc2s = (float)sqrt(1.0 - pow((double)beta2, (double)t));
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float pi = p[i];
     float gi = g[i] * coef;
@@ -86,13 +87,12 @@ int ep_adam_clip_step_f32(size_t n, float* p, const float* g, float* m, float* v
   if (n == 0) return EP_OK;
   EP_REQUIRE(p && g && m && v, "null pointer");
   EP_REQUIRE(step >= 1 || hyper_dev, "step counts from 1");
-  const double bc1 = 1.0 - pow((double)beta1, (double)(step >= 1 ? step : 1));
-  const double bc2_sqrt = sqrt(1.0 - pow((double)beta2, (double)(step >= 1 ? step : 1)));
   size_t grid = (n + 255) / 256;
   const size_t cap = (size_t)ep::sm_count() * 8;
   if (grid > cap) grid = cap;
   adam_clip_kernel<<<(unsigned)grid, 256, 0, ep::as_stream(stream)>>>(n, p, g, m, v, lr, hyper_dev, beta1, beta2, eps,
-                                                                     weight_decay, bc1, bc2_sqrt, max_norm, sq_norm);
+                                                                     weight_decay, step >= 1 ? step : 1, max_norm,
+                                                                     sq_norm);
   EP_LAUNCH_CHECK("adam_clip_kernel");
   return EP_OK;
 }

@@ -65,6 +65,9 @@ class ShardedTrainStepEngine(TrainStepEngine):
     def __init__(self, h_local, U_base_local, plans, params: FlatParams, cfg: StepConfig, lam_target=None,
                  mlp_mode="fp32", group=None, symmetric=True, pairs=None):
         dev = h_local.device
+        if not symmetric:
+            raise NotImplementedError("the vertex-sharded step needs symmetric K, M (FEM / tufted Laplacians): the "
+                                      "transposed products of a non-symmetric operator would need a halo scatter-add")
         self.plans, self.group = plans, group
         if pairs is None:
             pairs = [OperatorPair(pl.K_local, pl.M_local, dev, assume_symmetric=symmetric) for pl in plans]

@@ -113,9 +113,7 @@ class TrainStepEngine:
         self.U_pred = torch.empty((self.n_total, k), **f32)
         self.KU = torch.empty((self.n_total, k), **f32)
         self.MU = torch.empty((self.n_total, k), **f32)
-        self.KU_bar = torch.empty((self.n_total, k), **f32)
-        self.MU_bar = torch.empty((self.n_total, k), **f32)
-        self.D = torch.empty((self.n_total, k), **f32)
+        self._bwd_scratch = None       # KU_bar, MU_bar, D: only the unfused (non-symmetric) backward needs them
         self.dCorr = torch.empty((self.n_total, k), **f32)
         ws = ops.EigenWorkspace.get(k, self.dev)
         self.partials = [torch.empty(ws.plen, dtype=torch.float64, device=self.dev) for _ in pairs]
@@ -129,6 +127,7 @@ class TrainStepEngine:
         elif mlp_mode == "bf16":
             from .mlp_tc import TcMlp
             self.mlp = TcMlp(self.n_total, params, self.dev, h)
+            self.mlp.want_corr = False
         else:
             raise ValueError("mlp_mode must be 'fp32' or 'bf16'")
         self.launches_per_step = None
@@ -148,7 +147,6 @@ class TrainStepEngine:
 
     def loss_forward(self):
         c = self.cfg
-        self.loss_acc.zero_()
         for li, pair in enumerate(self.pairs):
             s = self._level_slices(li)
             ops.spmm2(pair, self.U_pred[s], out_K=self.KU[s], out_M=self.MU[s])
@@ -156,7 +154,8 @@ class TrainStepEngine:
             self._reduce_partials(li)
             ops.eigen_finalize(self.k, self._n_global(li), self.partials[li], c.w_res, c.w_orth, self.loss_acc,
                                coef=self.coefs[li], lam_out=self.lams[li], level0=(li == 0),
-                               lam_target=self.lam_target, w_trace=c.w_trace, w_order=c.w_order, w_eigen=c.w_eigen)
+                               lam_target=self.lam_target, w_trace=c.w_trace, w_order=c.w_order, w_eigen=c.w_eigen,
+                               overwrite=(li == 0))
 
     def loss_backward(self, scale, scale_dev=None):
         for li, pair in enumerate(self.pairs):
@@ -164,10 +163,11 @@ class TrainStepEngine:
             if self.fused_bwd and ops.eigen_bwd_fused_ok(pair, self.k, self.KU[s], self.MU[s], self.dCorr[s]):
                 ops.eigen_bwd_fused(pair, self.KU[s], self.MU[s], self.coefs[li], scale, self.dCorr[s], scale_dev)
                 continue
-            ops.eigen_bwd_prepare(self.U_pred[s], self.KU[s], self.MU[s], self.coefs[li], self.KU_bar[s],
-                                  self.MU_bar[s], self.D[s])
-            ops.spmm2_sum(pair.KT, pair.MT, self.KU_bar[s], self.MU_bar[s], self.D[s], scale, out=self.dCorr[s],
-                          scale_dev=scale_dev)
+            if self._bwd_scratch is None:
+                self._bwd_scratch = [torch.empty_like(self.KU) for _ in range(3)]
+            KU_bar, MU_bar, D = self._bwd_scratch
+            ops.eigen_bwd_prepare(self.U_pred[s], self.KU[s], self.MU[s], self.coefs[li], KU_bar[s], MU_bar[s], D[s])
+            ops.spmm2_sum(pair.KT, pair.MT, KU_bar[s], MU_bar[s], D[s], scale, out=self.dCorr[s], scale_dev=scale_dev)
 
     def optimizer_step(self, lr, hyper_dev=None):
         p, c = self.params, self.cfg
@@ -216,15 +216,15 @@ class TrainStepEngine:
 
     # ---- CUDA-graph replay: the whole step is captured once; per-step scalars live in device memory
     def _write_hyper(self, epoch, lr):
-        c, p = self.cfg, self.params
-        t = p.step_count + 1
+        """{float scale, float lr, int32 step} -> device.  The Adam bias corrections are derived from the integer
+        step inside the kernel (in double), exactly as in the eager launch, so replay == eager bit for bit."""
+        t = self.params.step_count + 1
         slot = self._hyper_slot = (self._hyper_slot + 1) % len(self._hyper_host)
         self._hyper_evt[slot].synchronize()          # the upload that last used this pinned slot has finished
         host = self._hyper_host[slot]
         host[0] = self.scale_for(epoch)
         host[1] = lr
-        host[2] = 1.0 - c.beta1 ** t
-        host[3] = (1.0 - c.beta2 ** t) ** 0.5
+        host.view(torch.int32)[2] = t
         self.hyper.copy_(host, non_blocking=True)
         self._hyper_evt[slot].record()
 
@@ -234,7 +234,7 @@ class TrainStepEngine:
         self.loss_forward()
         self.loss_backward(0.0, scale_dev=sd)
         self.mlp.backward(self.h, self.dCorr)
-        self.optimizer_step(0.0, hyper_dev=self.hyper[1:4])
+        self.optimizer_step(0.0, hyper_dev=self.hyper[1:3])
 
     def _step_graph(self, epoch, lr):
         if self.hyper is None:
@@ -252,9 +252,16 @@ class TrainStepEngine:
                 self._step_body_dev()
             self.launches_per_step = _cabi.launch_counter - before
             self._graph = g
+            self._captured_ptrs = self._io_ptrs()
+        elif self._io_ptrs() != self._captured_ptrs:
+            raise EpError("the captured step reads h / U_base at fixed addresses: copy new data INTO engine.h / "
+                          "engine.U_base (or call enable_graph() again) instead of rebinding them")
         self._graph.replay()
         self.params.step_count += 1
         return self.loss_acc
+
+    def _io_ptrs(self):
+        return (self.h.data_ptr(), self.U_base.data_ptr())
 
     def enable_graph(self, on=True):
         """Replay the step as one CUDA graph (call after a few eager warm-up steps).  Changing the shape of the
@@ -310,7 +317,8 @@ class HostFedPipeline:
         self.aggregate(self.x_dev[s], self.e.h)
         if hasattr(self.e.mlp, "input_changed"):
             self.e.mlp.input_changed(self.e.h)
-        self.e.U_base = self.u_dev[s]
+        # the engine (and a captured CUDA graph of its step) reads U_base at a FIXED address: copy, never rebind
+        self.e.U_base.copy_(self.u_dev[s], non_blocking=True)
         acc = self.e.step(epoch, lr)
         self.consumed[s].record(main)
         self.loss_host[s].copy_(acc, non_blocking=True)

@@ -1,6 +1,7 @@
 """bf16 tensor-core back end of the corrector MLP ("perf mode"): host-side buffer management around
 the tcgen05 kernels of csrc/mlp_tc.cu.  Same interface as engine.Fp32Mlp."""
 import ctypes
+import os
 
 import torch
 
@@ -32,9 +33,22 @@ def unpack_rows(packed, n, d_padded):
     return t.permute(0, 2, 1, 3).reshape(tiles * 128, d_padded)[:n].float()
 
 
+def _table(values, ctype=ctypes.c_void_p):
+    """Host array for the layer tables of ep_tc_chain_* (device pointers or ints inside)."""
+    arr = (ctype * len(values))()
+    for i, v in enumerate(values):
+        arr[i] = v if ctype is ctypes.c_int else (v.data_ptr() if v is not None else None)
+    return arr
+
+
 class TcMlp:
-    def __init__(self, n, params, device, h=None):
+    """chain=True (default): the whole forward is ONE launch (ep_tc_chain_fwd_bf16) and the dZ chain of the backward
+    is one launch (ep_tc_chain_dx_bf16) followed by one dW launch per layer; chain=False keeps the layer-by-layer
+    kernels (two gradient buffers instead of one per layer).  Both produce bit-identical results."""
+
+    def __init__(self, n, params, device, h=None, chain=None):
         self.p, self.n, self.dev = params, n, device
+        self.chain = (os.environ.get("EP_TC_LAYERWISE", "0") != "1") if chain is None else bool(chain)
         dims = params.dims                                    # [in, h1, ..., out]
         L = len(dims) - 1
         if L < 2:
@@ -51,7 +65,11 @@ class TcMlp:
         self.acts = [rows(self.pd[l + 1]) for l in range(L - 1)]             # outputs of hidden layers
         self.masks = [torch.zeros(query("ep_tc_relu_mask_bytes", n, self.pd[l + 1]), **u8) for l in range(L - 1)]
         wmax = max(self.pd[1:-1])
-        self.dz = [rows(wmax) for _ in range(2)]
+        if self.chain:
+            self.dzs = [rows(self.pd[l + 1]) for l in range(L - 1)]          # gradient w.r.t. every hidden pre-activation
+            self.dz = None
+        else:
+            self.dz = [rows(wmax) for _ in range(2)]
         self.dz_out = rows(self.pd[-1])
         self.Wp = [torch.zeros(query("ep_tc_packed_weight_bytes", self.pd[l + 1], self.pd[l]), **u8) for l in range(L)]
         self.WTp = [torch.zeros_like(w) for w in self.Wp]
@@ -62,6 +80,16 @@ class TcMlp:
         self.sm_count = torch.cuda.get_device_properties(device).multi_processor_count
         self.overlap = True
         self._packed_version = None
+        self.want_corr = True          # engine sets False: only U_pred is needed inside the training step
+        if self.chain:
+            self._t_pd = _table(self.pd, ctypes.c_int)
+            self._t_out = _table(dims[1:], ctypes.c_int)
+            self._t_Wp, self._t_b = _table(self.Wp), _table(list(self.p.b))
+            self._t_acts, self._t_masks = _table(self.acts), _table(self.masks)
+            self._t_bpd = _table(self.pd[::-1][:L], ctypes.c_int)           # pd[L], pd[L-1], ..., pd[1]
+            self._t_WT = _table([self.WTp[l] for l in range(L - 1, 0, -1)])
+            self._t_bmasks = _table([self.masks[l] for l in range(L - 2, -1, -1)])
+            self._t_dzs = _table([self.dzs[l] for l in range(L - 2, -1, -1)])
         if h is not None:
             self.input_changed(h)
 
@@ -79,6 +107,12 @@ class TcMlp:
         if self._packed_version != (h.data_ptr(), h._version):
             self.input_changed(h)
         self._pack_weights()
+        if self.chain:
+            corr = self.corr if (self.want_corr or U_pred is None) else None
+            call("ep_tc_chain_fwd_bf16", self.n, self.L, self._t_pd, self._t_out, _p(self.x0), self._t_Wp, self._t_b,
+                 self._t_acts, self._t_masks, _p(corr), self.corr.stride(0), _p(U_base), float(scale), _p(scale_dev),
+                 _p(U_pred), U_pred.stride(0) if U_pred is not None else 0, _stream())
+            return self.corr
         x = self.x0
         for l in range(self.L - 1):
             call("ep_tc_linear_fwd_bf16", self.n, self.pd[l], self.dims[l + 1], self.pd[l + 1], _p(x), _p(self.Wp[l]),
@@ -98,6 +132,16 @@ class TcMlp:
         main = torch.cuda.current_stream()
         side = self.side_stream
         pack_rows(d_out, self.pd[-1], out=self.dz_out)
+        if self.chain:
+            if L > 1:
+                call("ep_tc_chain_dx_bf16", self.n, L - 1, self._t_bpd, _p(self.dz_out), self._t_WT, self._t_bmasks,
+                     self._t_dzs, _stream())
+            for l in range(L - 1, -1, -1):
+                dz, dz_w = (self.dz_out, self.pd[-1]) if l == L - 1 else (self.dzs[l], self.pd[l + 1])
+                act = self.acts[l - 1] if l > 0 else self.x0
+                call("ep_tc_linear_dw_bf16", self.n, self.dims[l + 1], self.dims[l], dz_w, self.pd[l], _p(dz), _p(act),
+                     _p(self.p.dW[l]), _p(self.p.db[l]), _p(self.ws), self.ws_bytes, 0, _stream())
+            return
         dz, dz_w = self.dz_out, self.pd[-1]
         half = max(1, self.sm_count // 2)
         for l in range(L - 1, -1, -1):

@@ -143,11 +143,13 @@ def eigen_partials(U, KU, MU, out=None):
 
 
 def eigen_finalize(k, n_global, P, w_res, w_orth, loss_acc, coef=None, lam_out=None, level0=False,
-                   lam_target=None, w_trace=0.0, w_order=0.0, w_eigen=0.0, lam_bar_extra=None):
+                   lam_target=None, w_trace=0.0, w_order=0.0, w_eigen=0.0, lam_bar_extra=None, overwrite=False):
+    """level0: add the eigenvalue terms (:326-348); overwrite: loss_acc is set, not accumulated (first level)."""
     ws = EigenWorkspace.get(k, P.device)
     coef = coef if coef is not None else torch.empty(ws.clen, dtype=torch.float32, device=P.device)
     lam_out = lam_out if lam_out is not None else torch.empty(k, dtype=torch.float32, device=P.device)
-    call("ep_eigen_finalize_f32", k, float(n_global), _ptr(P), float(w_res), float(w_orth), int(bool(level0)),
+    flags = (1 if level0 else 0) | (2 if overwrite else 0)
+    call("ep_eigen_finalize_f32", k, float(n_global), _ptr(P), float(w_res), float(w_orth), flags,
          _ptr(lam_target), float(w_trace), float(w_order), float(w_eigen), _ptr(lam_bar_extra), _ptr(lam_out),
          _ptr(coef), _ptr(loss_acc), _stream())
     return lam_out, coef
@@ -336,7 +338,7 @@ def grad_sqnorm(g, out):
 
 
 def adam_clip_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, max_norm, sq_norm, hyper_dev=None):
-    """hyper_dev: device tensor {lr, 1 - beta1^t, sqrt(1 - beta2^t)} overriding lr / step (graph replay)."""
+    """hyper_dev: 8-byte device buffer {float lr, int32 step} overriding lr / step (graph replay)."""
     call("ep_adam_clip_step_f32", p.numel(), _ptr(p), _ptr(g), _ptr(m), _ptr(v), float(lr), _ptr(hyper_dev),
          float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(max_norm), _ptr(sq_norm),
          _stream())

@@ -76,10 +76,16 @@ class CsrMatrix:
         obj._T, obj._symmetric = None, None
         return obj
 
+    def _need_host(self, what):
+        if self._host is None:
+            raise ValueError("CsrMatrix.%s needs the host copy, which device-built matrices (from_device_arrays / "
+                             "from_edge_index) do not keep: pass symmetric=True/False to from_device_arrays" % what)
+        return self._host
+
     @property
     def symmetric(self):
         if self._symmetric is None:
-            A = self._host
+            A = self._need_host("symmetric")
             if A.shape[0] != A.shape[1]:
                 self._symmetric = False
             else:
@@ -93,7 +99,7 @@ class CsrMatrix:
         if self.symmetric:
             return self
         if self._T is None:
-            T = self._host.T.tocsr()
+            T = self._need_host("transpose()").T.tocsr()
             T.sort_indices()
             self._T = CsrMatrix(T, self.device)
         return self._T
@@ -119,7 +125,7 @@ class OperatorPair:
         if self.symmetric:
             self.KT, self.MT = self.K, self.M
         else:
-            KT, MT = self.K._host.T.tocsr(), self.M._host.T.tocsr()
+            KT, MT = self.K._need_host("transpose()").T.tocsr(), self.M._need_host("transpose()").T.tocsr()
             self.KT, self.MT = CsrMatrix(_sorted(KT), device), CsrMatrix(_sorted(MT), device)
 
     def _unify(self):

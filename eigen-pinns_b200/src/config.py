@@ -20,7 +20,8 @@ OPTIONAL_FIELDS = {
     "fps_start": None,         # explicit FPS start vertex (reference draws it unseeded)
     "seed": None,              # torch seed for the corrector initialisation (reference never seeds)
     "cgc_mode": "reference",   # "reference": dense coarse solve as in the reference | "skip"
-    "operator_type": "auto",   # "auto": point-cloud Laplacian if robust_laplacian exists, else FEM
+    "operator_type": "auto",   # level operators of the point samplers: "point_cloud" (robust_laplacian, as the
+                               # reference), "fem" (Galerkin P^T K P of the mesh's FEM operators), "auto" (first if installed)
 }
 
 

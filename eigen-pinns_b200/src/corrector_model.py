@@ -54,12 +54,31 @@ def _run_net(net, h, training):
 
 
 class _GraphCache:
+    """Remembers the CSR graph and the concatenated input [x | agg] of the last call.  An entry is reused only
+    for the SAME tensor object at the same in-place version; the cache keeps a strong reference to the keyed
+    tensors, so neither their storage nor their id() can be recycled for a different tensor while the entry
+    lives (the reference recomputes the aggregation on every call)."""
+
     def __init__(self):
-        self.key, self.csr, self.hkey, self.h = None, None, None, None
+        self.graph_obj, self.graph_ver, self.n, self.csr = None, None, None, None
+        self.x_obj, self.x_ver, self.h = None, None, None
 
     @staticmethod
-    def _tkey(t):
-        return (t.data_ptr(), tuple(t.shape), t._version, str(t.device))
+    def _ver(t):
+        return t._version if torch.is_tensor(t) else 0
+
+    def graph_hit(self, obj, n):
+        return self.graph_obj is obj and self.graph_ver == self._ver(obj) and self.n == n
+
+    def set_graph(self, obj, n, csr):
+        self.graph_obj, self.graph_ver, self.n, self.csr = obj, self._ver(obj), n, csr
+        self.x_obj, self.x_ver, self.h = None, None, None
+
+    def input_hit(self, x):
+        return self.x_obj is x and self.x_ver == x._version
+
+    def set_input(self, x, h):
+        self.x_obj, self.x_ver, self.h = x, x._version, h
 
 
 class SimpleCorrector(nn.Module):
@@ -70,14 +89,12 @@ class SimpleCorrector(nn.Module):
 
     def corrector_input(self, x, edge_index):
         c = self._cache
-        gkey = c._tkey(edge_index) + (x.shape[0],)
-        if c.key != gkey:
-            c.csr, c.key, c.hkey = _sparse.CsrMatrix.from_edge_index(edge_index, x.shape[0], x.device), gkey, None
+        if not c.graph_hit(edge_index, x.shape[0]):
+            c.set_graph(edge_index, x.shape[0], _sparse.CsrMatrix.from_edge_index(edge_index, x.shape[0], x.device))
         if x.requires_grad:
             raise NotImplementedError("gradients w.r.t. the node features are not part of the hot path")
-        hkey = c._tkey(x)
-        if c.hkey != hkey:
-            c.h, c.hkey = _ops.neighbor_mean_concat(x, c.csr), hkey
+        if not c.input_hit(x):
+            c.set_input(x, _ops.neighbor_mean_concat(x, c.csr))
         return c.h
 
     def forward(self, x, edge_index):
@@ -92,18 +109,14 @@ class SpectralCorrector(nn.Module):
 
     def corrector_input(self, x, A_norm_sparse):
         c = self._cache
-        if isinstance(A_norm_sparse, _sparse.CsrMatrix):
-            csr, gkey = A_norm_sparse, id(A_norm_sparse)
-        else:
-            gkey = (id(A_norm_sparse), tuple(A_norm_sparse.shape))
-            csr = c.csr if c.key == gkey else _sparse.CsrMatrix.from_torch_sparse(A_norm_sparse, x.device)
-        if c.key != gkey:
-            c.csr, c.key, c.hkey = csr, gkey, None
-        hkey = c._tkey(x)
-        if c.hkey != hkey:
+        if not c.graph_hit(A_norm_sparse, x.shape[0]):
+            csr = A_norm_sparse if isinstance(A_norm_sparse, _sparse.CsrMatrix) else \
+                _sparse.CsrMatrix.from_torch_sparse(A_norm_sparse, x.device)
+            c.set_graph(A_norm_sparse, x.shape[0], csr)
+        if not c.input_hit(x):
             if x.requires_grad:
                 raise NotImplementedError("gradients w.r.t. the node features are not part of the hot path")
-            c.h, c.hkey = _ops.spmm_concat(x.detach(), c.csr), hkey
+            c.set_input(x, _ops.spmm_concat(x.detach(), c.csr))
         return c.h
 
     def forward(self, x: torch.Tensor, A_norm_sparse) -> torch.Tensor:

@@ -60,6 +60,9 @@ class Sampler:
         self.hierarchy = config.hierarchy
         self.coarse_mesh_files = getattr(config, "coarse_mesh_files", None)
         self.fps_start = getattr(config, "fps_start", None)
+        self.operator_type = getattr(config, "operator_type", "auto")
+        if self.operator_type not in ('auto', 'point_cloud', 'fem'):
+            raise ValueError(f"operator_type must be 'auto', 'point_cloud' or 'fem', got '{self.operator_type}'")
         self.meshes, self.X_list, self.K_list, self.M_list = [], [], [], []
         self.P_list, self.U_list, self.actual_hierarchy = [], [], []
         self.edge_index_list, self.indices_per_level = [], []
@@ -105,10 +108,35 @@ class Sampler:
         else:
             self.indices_per_level = self._grid_coarsening(mesh, hierarchy)
             self.meshes.append(mesh)
+            point_cloud = self._use_point_cloud_operators()
             for idx in self.indices_per_level.values():
                 X = mesh.verts[idx]
-                K, M = mesh_helpers.compute_laplacian_and_mass_matrices(X)
+                if point_cloud:
+                    K, M = mesh_helpers.compute_laplacian_and_mass_matrices(X)
+                else:
+                    K, M = self._galerkin_operators(mesh, X)
                 self._push_level(X, K, M)
+
+    def _use_point_cloud_operators(self):
+        """operator_type 'point_cloud': the reference's robust_laplacian operators (ImportError if the package is
+        missing); 'fem': Galerkin restrictions of the mesh's FEM operators; 'auto': the former when robust_laplacian
+        is installed, else the latter, so the default configuration runs without the third-party package."""
+        if self.operator_type == 'fem':
+            return False
+        if self.operator_type == 'point_cloud':
+            return True
+        import importlib.util
+        return importlib.util.find_spec("robust_laplacian") is not None
+
+    def _galerkin_operators(self, mesh, X):
+        """(P^T K P, P^T M P) for a sub-sampled level: K, M the FEM operators of the full mesh (Mesh.py:348-364), P
+        the kNN inverse-distance interpolation from the level's points to the mesh vertices (utils.py:39-60).  P has
+        unit row sums, so constants stay in the null space of the coarse stiffness matrix."""
+        K, M = mesh_helpers.compute_stiffness_and_mass_matrices(mesh)
+        if X.shape[0] == mesh.verts.shape[0]:
+            return K, M
+        P = utils.build_prolongation(X, mesh.verts, k=min(self.prolongation_neighbors, X.shape[0])).tocsr()
+        return (P.T @ K.tocsr() @ P).tocoo(), (P.T @ M.tocsr() @ P).tocoo()
 
     def _assemble_edge_list(self):
         if self.sampler_type == 'graph_coarsening' and self.edge_computation_type == 'connectivity_based':
@@ -119,8 +147,10 @@ class Sampler:
     def _assemble_P_U(self):
         if self.sampler_type == 'graph_coarsening':
             _, U0, _, _ = utils.solve_eigenvalue_mesh(self.meshes[0], self.n_modes)
-        else:
+        elif self._use_point_cloud_operators():
             _, U0, _, _ = utils.solve_eigenvalue_point_cloud(self.X_list[0], self.n_modes)
+        else:
+            _, U0 = utils.solve_eigenvalue_operators(self.K_list[0], self.M_list[0], self.n_modes)
         self.U_list.append(U0)
         U_prev = U0.copy()
         for lv in range(1, len(self.X_list)):

@@ -108,6 +108,18 @@ def solve_eigenvalue_point_cloud(X, n_modes):
     return vals, np.array(vecs), L, M
 
 
+def solve_eigenvalue_operators(K, M, n_modes):
+    """Smallest generalised eigenpairs of a given (K, M) pair (shift-invert Lanczos; dense for tiny levels)."""
+    n = K.shape[0]
+    if n_modes >= n - 1:
+        from scipy.linalg import eigh
+        vals, vecs = eigh(K.toarray(), M.toarray())
+        return vals[:n_modes], vecs[:, :n_modes]
+    vals, vecs = eigsh(K.tocsc(), k=n_modes, M=M.tocsc(), sigma=-1e-8, which='LM')
+    order = np.argsort(vals)
+    return vals[order], np.array(vecs[:, order])
+
+
 def solve_eigenvalue_mesh(mesh, n_modes):
     from mesh_helpers import compute_stiffness_and_mass_matrices
     K, M = compute_stiffness_and_mass_matrices(mesh)

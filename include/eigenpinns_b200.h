@@ -10,8 +10,9 @@
  * Conventions
  *   - plain pointers and sizes only; no torch / C++ types cross the boundary
  *   - all array pointers are DEVICE pointers unless the function name ends in _host; the tiny
- *     parameter arrays `dims`, `lo` (voxel grid) and `bias` / `W` / `dW` / `db` pointer tables are
- *     HOST arrays (of device pointers where they are tables)
+ *     parameter arrays `dims`, `lo` (voxel grid) and the layer tables of ep_tc_chain_* are HOST arrays
+ *   - one device and one stream per process are assumed by the cached launch configuration
+ *     (SM count, opted-in shared-memory sizes, the gradient-norm scratch)
  *   - dense matrices are row-major with an explicit leading dimension (elements)
  *   - CSR: int32 rowptr[n+1], int32 col[nnz], fp32 val[nnz]
  *   - every call takes the CUDA stream it is enqueued on (cudaStream_t as void*); nothing
@@ -95,8 +96,9 @@ EP_API int ep_spmm_concat_f32(int n, int d, const int32_t* rowptr, const int32_t
  *   out[k*k + 1k ..)     sKK[j]    = sum_i KU[i,j]^2
  *   out[k*k + 2k ..)     sKM[j]    = sum_i KU[i,j] * MU[i,j]
  *   out[k*k + 3k ..)     sMM[j]    = sum_i MU[i,j]^2
- * (the last three give sum_i (KU - lam MU)^2 of :317-318 without a second pass; they are
- * accumulated in fp64 so the expansion does not cancel).  Partials of all ranks are summed
+ * (the last three give sum_i (KU - lam MU)^2 of :317-318 without a second pass; num and these
+ * three are accumulated in fp64 from the first product on - products of fp32 values are exact in
+ * fp64 - so the expansion keeps ~9 digits when the residual is 1e-4 of |KU|, i.e. near convergence).  Partials of all ranks are summed
  * (allreduce) before phase 2.  Deterministic: fixed grid, fixed reduction order. */
 EP_API size_t ep_eigen_partials_len(int k);                        /* k*k + 4*k doubles */
 EP_API size_t ep_eigen_partials_workspace_bytes(int k);
@@ -109,18 +111,21 @@ EP_API int ep_eigen_partials_f32(int n, int k, const float* U, int ldu, const fl
  *   L_orth = sum_ab (G_ab - I_ab)^2 / k;  and for level 0 the eigenvalue terms of :326-348
  *   (trace = mean lam, order = sum relu(lam_j - lam_{j+1}), eigen = mean (lam - lam_target)^2).
  * loss_acc[0..5] += {w_res L_res, w_orth L_orth, w_trace trace, w_order order, w_eigen eigen, total}
+ *   (flags & EP_FINALIZE_OVERWRITE: "=" instead of "+=", for the first level of a step)
  * coef receives what the backward needs (layout below, fp32):
  *   coef[0] = c_res = 2 w_res / (n_global k)
  *   coef[1 .. 1+k)      lam
  *   coef[1+k .. 1+2k)   num_bar   (dL/dnum)
  *   coef[1+2k .. 1+3k)  den_bar   (dL/dden)
  *   coef[1+3k .. )      G_bar[a*k+b] = 2 w_orth / k * (G_ab - I_ab)
- * lam_target may be NULL (eigen term = 0).  level0 != 0 enables the :326-348 terms.
+ * lam_target may be NULL (eigen term = 0).  flags & EP_FINALIZE_EIGENVALUE_TERMS enables the :326-348
+ * terms (the reference applies them to level 0 only).
  * lam_bar_extra (k floats, may be NULL) is added to dL/dlam: the gradient arriving from any
  * further use of the returned eigenvalues (autograd path of the drop-in modules). */
+enum ep_finalize_flags { EP_FINALIZE_EIGENVALUE_TERMS = 1, EP_FINALIZE_OVERWRITE = 2 };
 EP_API size_t ep_eigen_coef_len(int k);                            /* 1 + 3k + k*k floats */
 EP_API int ep_eigen_finalize_f32(int k, double n_global, const double* partials, float w_res, float w_orth,
-                          int level0, const float* lam_target, float w_trace, float w_order,
+                          int flags, const float* lam_target, float w_trace, float w_order,
                           float w_eigen, const float* lam_bar_extra, float* lam_out, float* coef,
                           double* loss_acc, ep_stream_t stream);
 
@@ -203,6 +208,24 @@ EP_API int ep_tc_linear_final_bf16(int n, int in_padded, int out, int out_padded
  * SMs each and the same tile order, so the dZ tiles one of them pulls from HBM are L2 hits for the other). */
 EP_API int ep_tc_linear_dx_bf16(int n, int out_padded, int in_padded, const void* dZ_packed, const void* WTp,
                          const void* relu_mask, void* dZprev_packed, int max_ctas, ep_stream_t stream);
+/* All layers in ONE launch ("fused MLP over vertex tiles", corrector_model.py:12-21,31): a persistent CTA takes two
+ * 128-vertex tiles through every layer; the activation tile stays in shared memory between layers (the epilogue of
+ * layer l writes the A operand of layer l+1 in place), weights stream from L2 in 16 KB K-slabs shared by both tiles.
+ * Hidden activations and ReLU masks are still written to HBM (the backward needs them) but never read back.
+ * Layer tables are HOST arrays of n_layers entries (device pointers inside): dims_padded[n_layers + 1] padded widths
+ * (input first), dims_out[n_layers] true output widths (bias lengths; dims_out[n_layers-1] = k), Wp / bias per layer,
+ * act_out / relu_mask_out per hidden layer (tables or entries may be NULL: not stored).  The last layer writes fp32
+ * rows: corr (may be NULL) and, fused, U_pred = U_base + scale * corr (multigrid_model.py:243-245).
+ * Results are bit-identical to the layer-by-layer entry points above. */
+EP_API int ep_tc_chain_fwd_bf16(int n, int n_layers, const int* dims_padded, const int* dims_out, const void* A0_packed,
+                         const void* const* Wp, const float* const* bias, void* const* act_out,
+                         void* const* relu_mask_out, float* corr, int ldc, const float* U_base, float scale,
+                         const float* scale_dev, float* U_pred, int ldu, ep_stream_t stream);
+/* Gradient chain dZ_{L-1} -> dZ_{L-2} -> ... in one launch: layer j computes dZ_out[j] = (dZ_in W) * [act > 0] with
+ * WTp[j] the packed transpose ([K/8][N][8], K = dims_padded[j], N = dims_padded[j+1]) and relu_mask[j] the bit mask the
+ * forward wrote for the activation of width dims_padded[j+1].  Every dZ_out[j] is stored (the dW kernels read them). */
+EP_API int ep_tc_chain_dx_bf16(int n, int n_layers, const int* dims_padded, const void* dZ_packed, const void* const* WTp,
+                        const void* const* relu_mask, void* const* dZ_out, ep_stream_t stream);
 /* dW = dZ^T act (fp32 [out x in]) and db = column sums of dZ; deterministic two-stage reduction. */
 EP_API size_t ep_tc_dw_workspace_bytes(void);
 EP_API int ep_tc_linear_dw_bf16(int n, int out, int in, int out_padded, int in_padded, const void* dZ_packed,
@@ -215,8 +238,10 @@ EP_API int ep_tc_linear_dw_bf16(int n, int out, int in, int out_padded, int in_p
  *   coef   = min(1, max_norm / (norm + 1e-6));  g = coef * g + weight_decay * p
  *   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2
  *   p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
- * hyper_dev (device, may be NULL) = {lr, 1 - b1^t, sqrt(1 - b2^t)} overrides lr and the step-dependent
- * bias corrections, so a captured CUDA graph can follow the ReduceLROnPlateau schedule of :221-223. */
+ * The bias corrections 1 - b^t are evaluated on the device in double from the integer step t, whether t
+ * arrives by value or from device memory, so a replayed CUDA graph is bit-identical to eager launches.
+ * hyper_dev (device, may be NULL) = {float lr, int32 t} (8 bytes) overrides lr and step, so a captured
+ * graph can follow the ReduceLROnPlateau schedule of :221-223 and the step count. */
 EP_API int ep_grad_sqnorm_f32(size_t n, const float* g, double* sq_out, ep_stream_t stream);
 EP_API int ep_adam_clip_step_f32(size_t n, float* p, const float* g, float* m, float* v, float lr,
                           const float* hyper_dev, float beta1, float beta2, float eps,

@@ -156,3 +156,51 @@ def test_bf16_training_tracks_reference():
     hist = np.array(hist)
     np.testing.assert_allclose(hist, g[f"{t}_losses"], rtol=2.5e-2)
     np.testing.assert_allclose(hist[:, 0], g[f"{t}_losses"][:, 0], rtol=2e-3)
+
+
+@pytest.mark.parametrize("n,dims", [(1, [32, 128, 16]), (129, [50, 128, 16]), (777, [82, 256, 256, 32]),
+                                    (2500, [146, 256, 256, 256, 64]), (300, [25, 64, 64, 64, 16]),
+                                    (128 * 149 * 2 + 5, [82, 256, 128, 256, 10]),
+                                    (40000, [82, 256, 256, 256, 256, 256, 256, 32])])
+def test_chain_kernels_equal_layerwise(n, dims):
+    """The fused all-layer kernels (ep_tc_chain_fwd_bf16 / ep_tc_chain_dx_bf16) must reproduce the layer-by-layer
+    kernels BIT FOR BIT: same bf16 roundings, same K order of the fp32 accumulation in TMEM."""
+    engine, tcm = pkg("engine"), pkg("mlp_tc")
+    g = torch.Generator().manual_seed(n)
+    Ws = [torch.randn(dims[i + 1], dims[i], generator=g) / np.sqrt(dims[i]) for i in range(len(dims) - 1)]
+    bs = [0.1 * torch.randn(dims[i + 1], generator=g) for i in range(len(dims) - 1)]
+    h = torch.randn(n, dims[0], generator=g).to(dev())
+    k = dims[-1]
+    U = torch.randn(n, k, generator=g).to(dev())
+    d_out = (torch.randn(n, k, generator=g) / n).to(dev())
+    res = []
+    for chain in (False, True):
+        p = engine.FlatParams(Ws, bs, dev())
+        m = tcm.TcMlp(n, p, dev(), h, chain=chain)
+        m.overlap = False                       # same dW grid (all SMs) in both variants
+        up = torch.full_like(U, float("nan"))
+        corr = m.forward(h, U, 0.25, up).clone()
+        m.backward(h, d_out)
+        torch.cuda.synchronize()
+        res.append((corr, up, [a.clone() for a in m.acts], [a.clone() for a in m.masks], p.grad.clone()))
+    (c0, u0, a0, m0, g0), (c1, u1, a1, m1, g1) = res
+    assert torch.equal(c0, c1) and torch.equal(u0, u1)
+    for x, y in zip(a0, a1):
+        assert torch.equal(x, y)
+    for x, y in zip(m0, m1):
+        assert torch.equal(x, y)
+    assert torch.isfinite(g1).all() and torch.equal(g0, g1)
+
+
+def test_chain_forward_without_corr_output():
+    """Inside the training step only U_pred is written (corr = NULL)."""
+    engine, tcm = pkg("engine"), pkg("mlp_tc")
+    h, m32, m16, p32, p16 = _mlp_pair(1000, [82, 256, 256, 32], seed=11)
+    U = torch.randn(1000, 32, device=dev())
+    up_a, up_b = torch.empty_like(U), torch.empty_like(U)
+    c = m16.forward(h, U, 0.5, up_a).clone()
+    m16.want_corr = False
+    m16.corr.fill_(7.0)
+    m16.forward(h, U, 0.5, up_b)
+    assert torch.equal(up_a, up_b) and torch.equal(up_a, U + 0.5 * c)
+    assert (m16.corr == 7.0).all()
