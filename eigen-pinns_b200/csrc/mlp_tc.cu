@@ -123,6 +123,62 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// max(x, 0) and round-to-nearest bf16 of two values in ONE instruction (upper half = hi, lower half = lo)
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// ---- ReLU bit mask ------------------------------------------------------------------------------------------
+// One 32-bit word per (vertex row, block of 32 features).  Inside a block the features are stored as 16 packed
+// bf16x2 words w_0..w_15 (w_i = features 2i | 2i+1); bit i of the mask word = "feature 2i is > 0", bit 16 + i =
+// "feature 2i+1 is > 0", where > 0 refers to the STORED (ReLU'd, bf16) activation.  This order costs three integer
+// instructions per PAIR to build (the halves of a ReLU'd word have a clear sign bit, so adding 0x7FFF to each half
+// carries into bit 15 / 31 exactly when the half is non-zero) and four per pair to apply to a packed gradient word.
+__device__ __forceinline__ uint32_t relu_mask_apply(uint32_t w, uint32_t mask_word, int i) {
+  return w & (((mask_word >> i) & 0x00010001u) * 0xFFFFu);
+}
+// tcgen05.ld without the wait, and a wait that carries the destination registers as operands so that no use of
+// them can be scheduled above it: lets the load of the next 32 columns fly while the current ones are processed.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+      : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+        "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+        "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+        "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+      :: "memory");
+}
+// One 32-column block of a hidden-layer epilogue: v = fp32 accumulators of one vertex row.
+//   forward : w_i = bf16x2(relu(v + bias)), returns the ReLU mask word
+//   dX      : w_i = bf16x2(v) & mask
+__device__ __forceinline__ uint32_t epi_block_fwd(const uint32_t (&v)[32], const float4 (&b)[8], uint32_t (&w)[16]) {
+#pragma unroll
+  for (int g4 = 0; g4 < 8; ++g4) {
+    w[2 * g4] = pack_relu_bf16x2(__uint_as_float(v[4 * g4]) + b[g4].x, __uint_as_float(v[4 * g4 + 1]) + b[g4].y);
+    w[2 * g4 + 1] = pack_relu_bf16x2(__uint_as_float(v[4 * g4 + 2]) + b[g4].z, __uint_as_float(v[4 * g4 + 3]) + b[g4].w);
+  }
+  uint32_t acc[4] = {0u, 0u, 0u, 0u};             // four independent chains instead of one 16-deep dependency chain
+#pragma unroll
+  for (int i = 0; i < 16; ++i)                    // bit i <- lo half of w_i non-zero, bit 16 + i <- hi half
+    acc[i & 3] |= ((w[i] + 0x7FFF7FFFu) >> (15 - i)) & (0x00010001u << i);
+  return (acc[0] | acc[1]) | (acc[2] | acc[3]);
+}
+__device__ __forceinline__ void epi_block_dx(const uint32_t (&v)[32], uint32_t mask_word, uint32_t (&w)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    w[i] = relu_mask_apply(pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), mask_word, i);
+}
 
 enum LinearMode { MODE_HIDDEN = 0, MODE_DX = 1, MODE_FINAL = 2 };
 
@@ -277,29 +333,19 @@ __global__ void __launch_bounds__(LINEAR_THREADS, 1) tc_linear_kernel(LinearArgs
             }
             __syncwarp();
           } else {
+            uint32_t w[16];
             uint32_t bits = 0;
+            if (MODE == MODE_HIDDEN) {
+              float4 b4[8];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {                     // 4 chunks of 8 columns
-              const int c = cb * 4 + g;
-              float f[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-              if (MODE == MODE_HIDDEN) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  f[j] += bias_s[c * 8 + j];
-                  if (a.relu) f[j] = fmaxf(f[j], 0.f);
-                  bits |= (f[j] > 0.f ? 1u : 0u) << (g * 8 + j);
-                }
-              } else {                                        // MODE_DX: keep where the forward activation was > 0
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = ((mw[cb] >> (g * 8 + j)) & 1u) ? f[j] : 0.f;
-              }
-              uint4 o;
-              o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-              o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-              *reinterpret_cast<uint4*>(a.out_packed + tile_off + (size_t)c * CHUNK_BYTES) = o;
+              for (int j = 0; j < 8; ++j) b4[j] = *reinterpret_cast<const float4*>(bias_s + cb * 32 + 4 * j);
+              bits = epi_block_fwd(v, b4, w);
             }
+            else epi_block_dx(v, mw[cb], w);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)                       // 4 chunks of 8 columns
+              *reinterpret_cast<uint4*>(a.out_packed + tile_off + (size_t)(cb * 4 + g) * CHUNK_BYTES) =
+                  make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
             if (MODE == MODE_HIDDEN && a.mask_out) a.mask_out[(size_t)row * ncb + cb] = bits;
           }
         }
@@ -325,13 +371,16 @@ __global__ void __launch_bounds__(LINEAR_THREADS, 1) tc_linear_kernel(LinearArgs
 // Weights do not fit one SM (0.72 MB for 82->256x6->32), so they stream from L2 through a ring of 16 KB K-slabs;
 // two tiles advance in lock step so that every slab feeds two MMAs (M = 256 per weight pass halves the L2 traffic).
 // TMEM: tile 0 accumulates in columns [0, 256), tile 1 in [256, 512).
-// Warp roles: warp 0 = weight-slab TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue
-// (tile = (warp - 2) / 4, TMEM lane quadrant = warp % 4); the first epilogue thread also issues the input-tile
-// TMA of the next pair as soon as the last layer's MMAs have retired.
+// Warp roles: warp 0 = weight-slab TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..17 = epilogue
+// (TMEM lane quadrant = warp % 4, tile = ((warp - 2) / 4) % 2, column half = (warp - 2) / 8: four warps per
+// scheduler, because draining an accumulator is latency bound - TMEM load, convert, store - not issue bound);
+// the first epilogue thread also issues the input-tile TMA of the next pair as soon as the last layer's MMAs have
+// retired.  Measured per 256-wide layer and tile pair (clock64 trace, B200): 32 MMAs issue in 4300 clk.
 // Algorithmic HBM bytes per vertex (forward, 82->256x6->32): read 2*96, write 6*(2*256 + 32) + 2*4*32 -> 3.7 KB,
 // against 6.9 KB for the layer-by-layer kernels (every hidden activation was read back once).
 constexpr int CH_MAX_LAYERS = 8;
-constexpr int CH_THREADS = 320;
+constexpr int CH_CBW = 8;                // 32-column blocks per epilogue warp: 8 -> 8 epilogue warps, 4 -> 16
+constexpr int CH_THREADS = 64 + (8 / CH_CBW) * 256;
 constexpr int CH_STAGES = 5;
 constexpr int CH_SLAB_BYTES = 16384;          // K = 32 rows of a 256-wide weight matrix
 constexpr int CH_ACT_BYTES = 65536;           // one 128 x 256 bf16 tile
@@ -352,6 +401,7 @@ struct ChainArgs {
   float* corr; int ldc;    // forward, last layer: fp32 rows (corr may be NULL)
   const float* U_base; float* U_pred; int ldu; float scale; const float* scale_dev;
   int n_rows, n_out, relu;
+  unsigned long long* trace;   // optional timing trace of CTA 0 (clock64 stamps), experiments only
 };
 enum ChainMode { MODE_CHAIN_FWD = 0, MODE_CHAIN_DX = 1 };
 
@@ -367,7 +417,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_kernel(const __grid_co
   uint64_t* wempty = bars + CH_STAGES;        // [CH_STAGES]
   uint64_t* in_full = wempty + CH_STAGES;     // input tiles of a pair have landed
   uint64_t* acc_full = in_full + 1;           // all MMAs of one layer (both tiles) have retired
-  uint64_t* act_ready = acc_full + 1;         // 256 epilogue threads: next operand written, accumulators drained
+  uint64_t* act_ready = acc_full + 1;         // all epilogue threads: next operand written, accumulators drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(act_ready + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -376,7 +426,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_kernel(const __grid_co
     for (int s = 0; s < CH_STAGES; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
     mbar_init(in_full, 1);
     mbar_init(acc_full, 1);
-    mbar_init(act_ready, 256);
+    mbar_init(act_ready, CH_THREADS - 64);
     fence_barrier_init();
   }
   if (MODE == MODE_CHAIN_FWD) {
@@ -421,6 +471,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_kernel(const __grid_co
           if (l == 0) mbar_wait(in_full, pi & 1);
           if (g > 0) mbar_wait(act_ready, (g - 1) & 1);
           tc_fence_after();
+          if (a.trace && blockIdx.x == 0 && g < 64) a.trace[g * 8 + 0] = clock64();      // operands ready
           const int N = a.L[l].N;
           const uint32_t idesc = make_idesc(TILE_M, N, false, false);
           const uint32_t b_lbo = (uint32_t)N * 16;
@@ -441,12 +492,16 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_kernel(const __grid_co
             if (++stage == CH_STAGES) { stage = 0; phase ^= 1; }
           }
           umma_commit(acc_full);
+          if (a.trace && blockIdx.x == 0 && g < 64) a.trace[g * 8 + 1] = clock64();      // all MMAs issued
         }
       }
     }
   } else {
+    // 16 epilogue warps: TMEM lane quadrant q = warp % 4, tile t, column half hf (column blocks 4 hf .. 4 hf + 3)
+    const int e = warp - 2;
     const int q = warp & 3;
-    const int t = (warp - 2) >> 2;                   // which tile of the pair
+    const int t = (e >> 2) & 1;
+    const int hf = (CH_CBW == 4) ? (e >> 3) : 0;
     const int r = q * 32 + lane;
     uint8_t* act = t ? act1 : act0;
     const bool elected = (warp == 2 && lane == 0);
@@ -459,41 +514,65 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_kernel(const __grid_co
     };
     if (elected && (int)blockIdx.x < n_pairs) issue_input(blockIdx.x);
     const float scale = (MODE == MODE_CHAIN_FWD && a.scale_dev) ? *a.scale_dev : a.scale;
-    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
+    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u + (uint32_t)hf * (CH_CBW * 32u);
+    const bool vec_out = ((a.ldc | a.ldu | a.n_out) & 3) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(a.corr) | reinterpret_cast<uintptr_t>(a.U_base) |
+                           reinterpret_cast<uintptr_t>(a.U_pred)) & 15u) == 0;
     uint32_t g = 0;
     for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const int tile = 2 * pair + t;
       const bool valid = tile < a.n_tiles;            // warp-uniform
       const long long row = (long long)tile * TILE_M + r;
       for (int l = 0; l < L; ++l, ++g) {
-        const ChainLayer& Ly = a.L[l];
-        const int N = Ly.N, ncb = N >> 5;
+        // layer parameters into registers once (the parameter struct is indexed dynamically)
+        const int N = a.L[l].N, ncb = N >> 5;
+        const int my_cb = min(CH_CBW, ncb - CH_CBW * hf);   // column blocks of this warp (<= 0: none)
+        uint8_t* const out_packed = a.L[l].out_packed;
+        uint32_t* const mask_ptr = a.L[l].mask;
+        const float* bl = bias_s + l * 256 + hf * (CH_CBW * 32);
         const bool last = (l == L - 1);
-        uint32_t mw[8];
-        if (MODE == MODE_CHAIN_DX) {
+        const bool work = valid && my_cb > 0;            // warp-uniform
+        uint32_t mw[CH_CBW];
+        float4 ub[8];
+        const bool final_rows = MODE == MODE_CHAIN_FWD && last && work && row < a.n_rows;
+        if (MODE == MODE_CHAIN_DX && work) {             // ReLU mask words of this row, fetched before the MMAs finish
+          const uint32_t* mrow = mask_ptr + (size_t)row * ncb + CH_CBW * hf;
+          if ((my_cb & 3) == 0) {
 #pragma unroll
-          for (int w = 0; w < 8; ++w) mw[w] = (valid && w < ncb) ? __ldg(Ly.mask + (size_t)row * ncb + w) : 0u;
+            for (int w4 = 0; w4 < CH_CBW / 4; ++w4) {
+              const uint4 m0 = 4 * w4 < my_cb ? __ldg(reinterpret_cast<const uint4*>(mrow) + w4) : make_uint4(0u, 0u, 0u, 0u);
+              mw[4 * w4] = m0.x; mw[4 * w4 + 1] = m0.y; mw[4 * w4 + 2] = m0.z; mw[4 * w4 + 3] = m0.w;
+            }
+          } else {
+#pragma unroll
+            for (int w = 0; w < CH_CBW; ++w) mw[w] = w < my_cb ? __ldg(mrow + w) : 0u;
+          }
+        }
+        if (final_rows && vec_out && a.U_pred) {         // first 32 columns of the U_base row: in flight during the MMAs
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = hf * (CH_CBW * 32) + 4 * j;
+            ub[j] = col < a.n_out ? __ldg(reinterpret_cast<const float4*>(a.U_base + (size_t)row * a.ldu + col))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
         mbar_wait(acc_full, g & 1);
         tc_fence_after();
+        if (a.trace && blockIdx.x == 0 && g < 64 && threadIdx.x == 64) a.trace[g * 8 + 2] = clock64();   // accumulators ready
         if (last && elected) {                         // operand buffers are free: fetch the next pair's input now
           const int next = pair + (int)gridDim.x;
           if (next < n_pairs) issue_input(next);
         }
-        if (valid) {
+        if (work) {
           if (MODE == MODE_CHAIN_FWD && last) {
             // fp32 rows: every thread owns one vertex row and writes whole 128-byte lines of it
             const bool in_rows = row < a.n_rows;
-            const bool vec = ((a.ldc | a.ldu | a.n_out) & 3) == 0 &&
-                             ((reinterpret_cast<uintptr_t>(a.corr) | reinterpret_cast<uintptr_t>(a.U_base) |
-                               reinterpret_cast<uintptr_t>(a.U_pred)) & 15u) == 0;
-            const float* bl = bias_s + l * 256;
-            for (int cb = 0; cb < ncb; ++cb) {
-              float4 ub[8];
-              if (vec && in_rows && a.U_pred) {
+            for (int cb = 0; cb < my_cb; ++cb) {
+              const int col0 = hf * (CH_CBW * 32) + cb * 32;
+              if (cb > 0 && vec_out && in_rows && a.U_pred) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  const int col = cb * 32 + 4 * j;
+                  const int col = col0 + 4 * j;
                   ub[j] = col < a.n_out ? __ldg(reinterpret_cast<const float4*>(a.U_base + (size_t)row * a.ldu + col))
                                         : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
@@ -501,14 +580,15 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_kernel(const __grid_co
               uint32_t v[32];
               tmem_ld32(t_addr + cb * 32, v);
               if (in_rows) {
-                if (vec) {
+                if (vec_out) {
 #pragma unroll
                   for (int j = 0; j < 8; ++j) {
-                    const int col = cb * 32 + 4 * j;
+                    const int col = col0 + 4 * j;
                     if (col < a.n_out) {
+                      const float4 bj = *reinterpret_cast<const float4*>(bl + cb * 32 + 4 * j);
                       float4 c;
-                      c.x = __uint_as_float(v[4 * j]) + bl[col];         c.y = __uint_as_float(v[4 * j + 1]) + bl[col + 1];
-                      c.z = __uint_as_float(v[4 * j + 2]) + bl[col + 2]; c.w = __uint_as_float(v[4 * j + 3]) + bl[col + 3];
+                      c.x = __uint_as_float(v[4 * j]) + bj.x;     c.y = __uint_as_float(v[4 * j + 1]) + bj.y;
+                      c.z = __uint_as_float(v[4 * j + 2]) + bj.z; c.w = __uint_as_float(v[4 * j + 3]) + bj.w;
                       if (a.corr) *reinterpret_cast<float4*>(a.corr + (size_t)row * a.ldc + col) = c;
                       if (a.U_pred) {
                         float4 u;
@@ -521,9 +601,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_kernel(const __grid_co
                 } else {
 #pragma unroll
                   for (int j = 0; j < 32; ++j) {
-                    const int col = cb * 32 + j;
+                    const int col = col0 + j;
                     if (col < a.n_out) {
-                      const float c = __uint_as_float(v[j]) + bl[col];
+                      const float c = __uint_as_float(v[j]) + bl[cb * 32 + j];
                       if (a.corr) a.corr[(size_t)row * a.ldc + col] = c;
                       if (a.U_pred)
                         a.U_pred[(size_t)row * a.ldu + col] =
@@ -535,45 +615,51 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_kernel(const __grid_co
             }
           } else {
             const size_t tile_off = (size_t)tile * (N >> 3) * CHUNK_BYTES + (size_t)r * 16;
-            const float* bl = bias_s + l * 256;
             const bool to_smem = !last;
+            uint32_t bits[CH_CBW];
 #pragma unroll
-            for (int cb = 0; cb < 8; ++cb) {
-              if (cb < ncb) {
+            for (int cb = 0; cb < CH_CBW; ++cb) {
+              if (cb < my_cb) {
+                float4 b4[8];
+                if (MODE == MODE_CHAIN_FWD) {              // bias of these 32 columns: in flight with the TMEM load
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) b4[j] = *reinterpret_cast<const float4*>(bl + cb * 32 + 4 * j);
+                }
                 uint32_t v[32];
                 tmem_ld32(t_addr + cb * 32, v);
-                uint32_t bits = 0;
+                uint32_t w[16];
+                if (MODE == MODE_CHAIN_FWD) bits[cb] = epi_block_fwd(v, b4, w);
+                else epi_block_dx(v, mw[cb], w);
 #pragma unroll
                 for (int g4 = 0; g4 < 4; ++g4) {
-                  const int c = cb * 4 + g4;
-                  float f[8];
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g4 * 8 + j]);
-                  if (MODE == MODE_CHAIN_FWD) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                      f[j] += bl[c * 8 + j];
-                      if (a.relu) f[j] = fmaxf(f[j], 0.f);
-                      bits |= (f[j] > 0.f ? 1u : 0u) << (g4 * 8 + j);
-                    }
-                  } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) f[j] = ((mw[cb] >> (g4 * 8 + j)) & 1u) ? f[j] : 0.f;
-                  }
-                  uint4 o;
-                  o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-                  o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-                  if (to_smem) *reinterpret_cast<uint4*>(act + (size_t)c * CHUNK_BYTES + (size_t)r * 16) = o;
-                  if (Ly.out_packed) *reinterpret_cast<uint4*>(Ly.out_packed + tile_off + (size_t)c * CHUNK_BYTES) = o;
+                  const uint4 o = make_uint4(w[4 * g4], w[4 * g4 + 1], w[4 * g4 + 2], w[4 * g4 + 3]);
+                  const size_t c_off = (size_t)((hf * CH_CBW + cb) * 4 + g4) * CHUNK_BYTES;
+                  if (to_smem) *reinterpret_cast<uint4*>(act + c_off + (size_t)r * 16) = o;
+                  if (out_packed) *reinterpret_cast<uint4*>(out_packed + tile_off + c_off) = o;
                 }
-                if (MODE == MODE_CHAIN_FWD && Ly.mask) Ly.mask[(size_t)row * ncb + cb] = bits;
+              } else if (MODE == MODE_CHAIN_FWD) {
+                bits[cb] = 0u;
+              }
+            }
+            if (MODE == MODE_CHAIN_FWD && mask_ptr) {      // this warp's four mask words of the row in one 16-byte store
+              uint32_t* mrow = mask_ptr + (size_t)row * ncb + CH_CBW * hf;
+              if ((my_cb & 3) == 0) {
+#pragma unroll
+                for (int w4 = 0; w4 < CH_CBW / 4; ++w4)
+                  if (4 * w4 < my_cb)
+                    reinterpret_cast<uint4*>(mrow)[w4] = make_uint4(bits[4 * w4], bits[4 * w4 + 1], bits[4 * w4 + 2], bits[4 * w4 + 3]);
+              } else {
+#pragma unroll
+                for (int cb = 0; cb < CH_CBW; ++cb) if (cb < my_cb) mrow[cb] = bits[cb];
               }
             }
           }
         }
+        if (a.trace && blockIdx.x == 0 && g < 64 && threadIdx.x == 64) a.trace[g * 8 + 3] = clock64();   // drained
         if (!last) fence_proxy_async_smem();           // generic-proxy writes -> visible to the MMA (async proxy)
         tc_fence_before();
         mbar_arrive(act_ready);
+        if (a.trace && blockIdx.x == 0 && g < 64 && threadIdx.x == 64) a.trace[g * 8 + 4] = clock64();   // arrived
       }
     }
   }
@@ -883,9 +969,11 @@ int launch_chain(const ChainArgs& a, cudaStream_t st) {
     configured = true;
   }
   const int n_pairs = (a.n_tiles + 1) / 2;
+  ChainArgs b = a;
+  b.trace = reinterpret_cast<unsigned long long*>(((uintptr_t)(uint32_t)ep::tune_flag(4) << 32) | (uint32_t)ep::tune_flag(3));
   int grid = ep::sm_count();
   if (grid > n_pairs) grid = n_pairs;
-  tc_chain_kernel<MODE><<<grid, CH_THREADS, smem, st>>>(a);
+  tc_chain_kernel<MODE><<<grid, CH_THREADS, smem, st>>>(b);
   EP_LAUNCH_CHECK("tc_chain_kernel");
   return EP_OK;
 }
@@ -947,6 +1035,7 @@ int ep_tc_pack_weight_bf16(int out, int in, int out_padded, int in_padded, const
 int ep_tc_linear_fwd_bf16(int n, int in_padded, int out, int out_padded, const void* A_packed, const void* Wp,
                           const float* bias, int relu, void* out_packed, void* relu_mask_out, ep_stream_t stream) {
   EP_REQUIRE(n > 0 && A_packed && Wp && out_packed, "bad argument");
+  if (!relu) { ep::set_error("ep_tc_linear_fwd_bf16: hidden layers are Linear + ReLU (relu must be 1)"); return EP_ERR_UNSUPPORTED; }
   if (!dims_ok(in_padded, out_padded)) { ep::set_error("ep_tc_linear_fwd_bf16: padded dims must be multiples of 32 in [32, 256]"); return EP_ERR_UNSUPPORTED; }
   LinearArgs a{};
   a.A = static_cast<const uint8_t*>(A_packed); a.B = static_cast<const uint8_t*>(Wp);

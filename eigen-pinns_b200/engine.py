@@ -278,6 +278,30 @@ class TrainStepEngine:
         return self.step(epoch, lr).cpu().numpy()
 
 
+class LossReader:
+    """Pipelined read-back of the six loss terms: `push(acc)` enqueues a 48-byte D2H copy into a pinned ring and returns
+    a ticket, `get(ticket)` waits for that copy only.  Reading with a delay of one step keeps the host one step ahead
+    of the GPU, so the reference's `total_loss.item()` every epoch (src/multigrid_model.py:261) costs no bubble."""
+
+    def __init__(self, depth=4):
+        self.buf = [torch.empty(6, dtype=torch.float64).pin_memory() for _ in range(depth)]
+        self.evt = [torch.cuda.Event() for _ in range(depth)]
+        self.n = 0
+
+    def push(self, acc):
+        slot = self.n % len(self.buf)
+        self.buf[slot].copy_(acc, non_blocking=True)
+        self.evt[slot].record()
+        self.n += 1
+        return self.n - 1
+
+    def get(self, ticket):
+        assert self.n - ticket <= len(self.buf), "ticket expired (ring depth)"
+        slot = ticket % len(self.buf)
+        self.evt[slot].synchronize()
+        return self.buf[slot].numpy().copy()
+
+
 class HostFedPipeline:
     """End-to-end driver with HOST inputs every step: node features x (n x d) and the base subspace U_base
     (n x k) live in pinned host memory.  Uploads go through a copy stream into one of two staging sets, so the

@@ -19,7 +19,10 @@ OPTIONAL_FIELDS = {
     "mlp_mode": "fp32",        # "fp32" parity mode | "bf16" tcgen05 perf mode
     "fps_start": None,         # explicit FPS start vertex (reference draws it unseeded)
     "seed": None,              # torch seed for the corrector initialisation (reference never seeds)
-    "cgc_mode": "reference",   # "reference": dense coarse solve as in the reference | "skip"
+    "cgc_mode": "reference",   # "reference": dense coarse solve as in the reference | "regularized" | "skip"
+    "cgc_shift": 1e-3,         # "regularized": coarse solve with K_c + cgc_shift * M_c (block CG on the device)
+    "loss_read_delay": 1,      # epochs between launching a step and reading its loss (0 = synchronous like :261)
+    "cuda_graph": True,        # replay the epoch body as one CUDA graph after three eager epochs
     "operator_type": "auto",   # level operators of the point samplers: "point_cloud" (robust_laplacian, as the
                                # reference), "fem" (Galerkin P^T K P of the mesh's FEM operators), "auto" (first if installed)
 }

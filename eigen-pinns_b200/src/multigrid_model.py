@@ -45,6 +45,9 @@ class MultigridGNN:
             setattr(self, dst, getattr(config, src))
         self.mlp_mode = getattr(config, "mlp_mode", "fp32")
         self.cgc_mode = getattr(config, "cgc_mode", "reference")
+        self.cgc_shift = float(getattr(config, "cgc_shift", 1e-3))
+        self.loss_read_delay = int(getattr(config, "loss_read_delay", 1))
+        self.graph_after_epochs = 3 if getattr(config, "cuda_graph", True) else -1
         self.seed = getattr(config, "seed", None)
         self.loss_history = []
 
@@ -88,7 +91,7 @@ class MultigridGNN:
                 U_c, lam = U_fine, self._dev_f32(vals)
             else:
                 U_c, lam = self.apply_coarse_grid_correction(U_fine, K_list[i], M_list[i], K_list[i - 1],
-                                                             P_list[i - 1])
+                                                             P_list[i - 1], M_coarse=M_list[i - 1])
             U_out.append(U_c)
             lambdas.append(lam)
         vals0, _ = self.refine_eigenvectors(U_init_list[0], K_list[0], M_list[0])
@@ -184,9 +187,20 @@ class MultigridGNN:
         self.engine = engine
         best, stale, max_stale = float('inf'), 0, 5000
         self.model.train()
-        for epoch in range(self.epochs):
-            lr = optimizer.param_groups[0]['lr']
-            acc = engine.step(epoch, lr=lr).cpu().numpy()          # the one host sync per epoch
+        # The step is replayed as one CUDA graph after a few eager epochs, and the loss is read back with a delay of
+        # one epoch (pinned ring), so the host never stalls the GPU.  Consequence, documented deviation from the
+        # reference's synchronous `.item()` (:261): ReduceLROnPlateau and the early-stopping counter see the loss of
+        # epoch e while epoch e+1 is already in flight, i.e. a learning-rate change or a stop takes effect one epoch
+        # later.  `loss_read_delay = 0` restores the fully synchronous behaviour.
+        delay = int(getattr(self, "loss_read_delay", 1))
+        reader = _engine.LossReader(depth=4)
+        graph_after = int(getattr(self, "graph_after_epochs", 3))
+        pending = []                                                   # (epoch, ticket, scale)
+        stop = False
+
+        def consume(epoch, ticket, scale):
+            nonlocal best, stale, stop
+            acc = reader.get(ticket)
             total = float(acc[5])
             self.loss_history.append(total)
             scheduler.step(total)
@@ -196,10 +210,23 @@ class MultigridGNN:
                 stale += 1
             if stale > max_stale:
                 print(f"\nEarly stopping at epoch {epoch} (no improvement for {max_stale} epochs)")
-                break
+                stop = True
             if epoch % self.log_every == 0 or epoch == self.epochs - 1:
                 t = [torch.tensor(float(v)) for v in (acc[5], acc[0], acc[1], 0.0, acc[2], acc[3], acc[4])]
-                self._log_training_progress(epoch, *t, engine.scale_for(epoch))
+                self._log_training_progress(epoch, *t, scale)
+
+        for epoch in range(self.epochs):
+            if epoch == graph_after and graph_after >= 0:
+                engine.enable_graph()
+            lr = optimizer.param_groups[0]['lr']
+            acc = engine.step(epoch, lr=lr)
+            pending.append((epoch, reader.push(acc), engine.scale_for(epoch)))
+            while len(pending) > delay:
+                consume(*pending.pop(0))
+            if stop:
+                break
+        while pending and not stop:
+            consume(*pending.pop(0))
 
     def _forward_pass(self, x_feats, edge_index, A_norm):
         x_feats = x_feats.to(self.device)
@@ -248,9 +275,12 @@ class MultigridGNN:
         vals, C = eigh(A.to(torch.float32).cpu().numpy(), B.to(torch.float32).cpu().numpy())
         return vals, U.cpu().numpy() @ C
 
-    def apply_coarse_grid_correction(self, U_fine, K_fine, M_fine, K_coarse, P_np):
-        """U - P K_c^{-1} P^T (K U - M U diag(lambda)) with lambda from Rayleigh-Ritz.  The coarse solve is a
-        dense fp32 LU like the reference's and fails the same way on a singular K_c."""
+    def apply_coarse_grid_correction(self, U_fine, K_fine, M_fine, K_coarse, P_np, M_coarse=None):
+        """U - P A_c^{-1} P^T (K U - M U diag(lambda)) with lambda from Rayleigh-Ritz (reference :410-450).
+        cgc_mode 'reference': A_c = K_c, dense fp32 LU like the reference - fails the same way on a singular K_c
+        (FEM stiffness matrices of closed or multi-component meshes are singular).
+        cgc_mode 'regularized': A_c = K_c + cgc_shift * M_c (or + cgc_shift * I without M_c), never densified: Jacobi-
+        preconditioned block CG whose operator application is the CSR SpMM kernel, all k right-hand sides at once."""
         lam_np, _ = self.refine_eigenvectors(U_fine, K_fine, M_fine)
         lam = self._dev_f32(lam_np)
         U = self._dev_f32(U_fine)
@@ -258,10 +288,44 @@ class MultigridGNN:
         R_f = KU - MU * lam.unsqueeze(0)
         P = utils.device_operator(P_np, self.device)
         R_c = _ops.spmm(P.transpose(), R_f)
-        K_c = torch.from_numpy(np.asarray(K_coarse.todense(), dtype=np.float32)).to(self.device)
-        delta_c = torch.linalg.solve(K_c, R_c)
+        if self.cgc_mode == "regularized":
+            delta_c = self._coarse_solve_cg(K_coarse, M_coarse, R_c)
+        else:
+            K_c = torch.from_numpy(np.asarray(K_coarse.todense(), dtype=np.float32)).to(self.device)
+            delta_c = torch.linalg.solve(K_c, R_c)
         U_cgc = U - _ops.spmm(P, delta_c.contiguous())
         return U_cgc.detach(), lam.detach()
+
+    def _coarse_solve_cg(self, K_coarse, M_coarse, B, tol=1e-6, max_iter=5000):
+        """Solve (K_c + shift M_c) X = B for all columns of B (fp32, device).  Per iteration: one SpMM
+        (ep_spmm_csr_f32) and a handful of column reductions."""
+        import scipy.sparse as sp
+        Kc = sp.csr_matrix(K_coarse).astype(np.float64)
+        reg = sp.csr_matrix(M_coarse).astype(np.float64) if M_coarse is not None else sp.identity(Kc.shape[0], format="csr")
+        A_host = (Kc + self.cgc_shift * reg).tocsr()
+        A = utils.device_operator(A_host, self.device)
+        d_inv = self._dev_f32(1.0 / A_host.diagonal()).unsqueeze(1)
+        B = B.contiguous()
+        X = torch.zeros_like(B)
+        R = B.clone()
+        Z = d_inv * R
+        Pd = Z.clone()
+        rz = (R * Z).sum(0)
+        b_norm = B.norm(dim=0).clamp_min(1e-30)
+        self.cgc_iterations = 0
+        for it in range(max_iter):
+            AP = _ops.spmm(A, Pd)
+            alpha = rz / (Pd * AP).sum(0).clamp_min(1e-30)
+            X += Pd * alpha.unsqueeze(0)
+            R -= AP * alpha.unsqueeze(0)
+            self.cgc_iterations = it + 1
+            if it % 8 == 7 and float((R.norm(dim=0) / b_norm).max()) < tol:       # one host sync per 8 iterations
+                break
+            Z = d_inv * R
+            rz_new = (R * Z).sum(0)
+            Pd = Z + Pd * (rz_new / rz.clamp_min(1e-30)).unsqueeze(0)
+            rz = rz_new
+        return X
 
     def _refine_final_predictions(self, sampler, U_pred_all):
         hierarchy = sampler.actual_hierarchy

@@ -192,8 +192,10 @@ EP_API int ep_tc_pack_rows_bf16(int n, int d, int d_padded, const float* X, int 
 /* W fp32 [out x in] (nn.Linear layout) -> Wp [in_p/8][out_p][8] and, if WTp != NULL, WTp [out_p/8][in_p][8]. */
 EP_API int ep_tc_pack_weight_bf16(int out, int in, int out_padded, int in_padded, const float* W, void* Wp,
                            void* WTp, ep_stream_t stream);
-/* hidden layer: out_packed = relu?(A W^T + b); relu_mask_out (may be NULL) receives one bit per
- * activation, [row][out_padded/32] words, bit j of word w set iff activation 32w+j > 0. */
+/* hidden layer: out_packed = relu(A W^T + b) (relu must be 1); relu_mask_out (may be NULL) receives one bit per
+ * activation, [row][out_padded/32] words.  Bit order inside a word (block of 32 features = 16 stored bf16 pairs):
+ * bit i = "feature 32w + 2i is > 0", bit 16 + i = "feature 32w + 2i + 1 is > 0", > 0 referring to the stored bf16
+ * activation (this order makes building and applying the mask 1.5 / 2 integer instructions per element). */
 EP_API size_t ep_tc_relu_mask_bytes(int n, int d_padded);
 EP_API int ep_tc_linear_fwd_bf16(int n, int in_padded, int out, int out_padded, const void* A_packed, const void* Wp,
                           const float* bias, int relu, void* out_packed, void* relu_mask_out,

@@ -56,7 +56,10 @@ def test_tc_hidden_forward(n, d_in, d_out):
     err = (got - ref).abs().max().item()
     assert err <= 2.0 ** -7 * max(1.0, ref.abs().max().item()), err
     words = mask.view(torch.int32).view(-1, op // 32)[:n]
-    bits = ((words.unsqueeze(-1) >> torch.arange(32, device=dev())) & 1).reshape(n, op)[:, :d_out]
+    # bit i of a word = feature 2i of its 32-feature block, bit 16 + i = feature 2i + 1
+    pos = torch.arange(32, device=dev())
+    pos = (pos % 2) * 16 + pos // 2
+    bits = ((words.unsqueeze(-1) >> pos) & 1).reshape(n, op)[:, :d_out]
     assert torch.equal(bits.bool(), got > 0)
 
 
