@@ -35,9 +35,12 @@ WORKLOADS = {
     "torus4m": ("torus", 2048, 64),
 }
 HIDDEN = [256] * 6                               # reference default (src/parameters.yml)
-# dram__bytes_read.sum + dram__bytes_write.sum per launch / vertices of tc_linear_kernel<HIDDEN> from the committed
-# ncu --set full capture (profiles/r01_final_ncu_full_summary.csv: 0.5122 GB + 0.4900 GB at 998,562 vertices)
-NCU_TRAFFIC_HIDDEN_PER_VERTEX = (0.5122e9 + 0.4900e9) / 998562
+# dram__bytes_read.sum + dram__bytes_write.sum per launch / vertices from the committed ncu --set full captures
+# (profiles/r02_ncu_chain_summary.csv: tc_chain_kernel<FWD> 0.3313 GB + 3.3329 GB at 998,562 vertices, k = 32;
+#  profiles/r01_final_ncu_full_summary.csv: spmm_kernel<4,1> 0.4330 GB)
+NCU_TRAFFIC_CHAIN_FWD_PER_VERTEX = (0.331345e9 + 3.332921e9) / 998562
+NCU_TRAFFIC_SPMM2_PER_VERTEX = 0.4330e9 / 998562
+MIN_TIMED_MS = 1000.0                            # every timed region lasts at least this long (clock sampling, sustained rates)
 
 
 def pkg(name=None):
@@ -58,6 +61,10 @@ def build_host_workload(name):
     rng = np.random.default_rng(0)
     if kind == "icosphere":
         verts, tris = syn.icosphere(size)
+        # latitude-band vertex order: contiguous vertex ranges (one per GPU) then touch two neighbours each and the
+        # halos are balanced (the generator's face-by-face order put every icosahedron edge vertex on rank 0)
+        part = pkg("partition")
+        verts, tris = part.permute_mesh(verts, tris, part.z_order(verts))
         unit = verts.copy()
         verts = fem.normalize_verts(verts)
         modes, degs = syn.real_spherical_harmonics(unit, k)
@@ -130,50 +137,70 @@ def measured_peaks():
     return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
 
 
-# ------------------------------------------------------------------------------------------ reference arm
-def cpu_reference_steps_per_s(sample_name, full_vertices, steps, warmup, threads=None):
-    """Time the CPU oracle (torch-CPU port of the reference step, oracle/step_port.py) on a bounded sample
-    of the workload and scale to the full vertex count (the step is linear in the number of vertices)."""
+# ------------------------------------------------------------------------------------------ CPU oracle / reference arm
+def oracle_trainer(w):
+    """CPU oracle (torch-CPU port of the reference step, oracle/step_port.py) on a host workload."""
     import torch
     from oracle import step_port
-    if threads:
-        torch.set_num_threads(threads)
-    w = build_host_workload(sample_name)
-    n, k = w["verts"].shape[0], w["k"]
+    k = w["k"]
     U_base = step_port.m_normalize(torch.from_numpy(w["U0"]), w["M"])
     ei = torch.from_numpy(w["edges"])
     lam = torch.zeros(k)
     x = step_port.level_features(w["verts"], U_base, torch.linspace(0, 1, k), ei, w["K"], w["M"], 0, 1)
     tr = step_port.CorrectorTrainer(x, ei, U_base, [w["K"]], [w["M"]], lam, HIDDEN, k)
     tr.epoch = 2500
-    for _ in range(warmup):
-        tr.step()
+    return tr
+
+
+def time_oracle(w, steps, warmup, threads, budget_s=None):
+    """Wall-clock steps/s of the oracle on all host cores.  With a time budget the number of timed steps is cut
+    (never below 2) and the number actually executed is reported - nothing is extrapolated."""
+    import torch
+    if threads:
+        torch.set_num_threads(threads)
+    tr = oracle_trainer(w)
     t0 = time.perf_counter()
-    for _ in range(steps):
+    for _ in range(max(1, warmup)):
         tr.step()
-    dt = (time.perf_counter() - t0) / steps
-    scale = full_vertices / n
-    return dict(sample_ms=dt * 1e3, sample_vertices=n, ms_per_step=dt * 1e3 * scale, steps_per_s=1.0 / (dt * scale),
-                threads=torch.get_num_threads())
+    t_warm = (time.perf_counter() - t0) / max(1, warmup)
+    n = steps
+    if budget_s is not None:
+        n = max(2, min(steps, int(budget_s / max(t_warm, 1e-6))))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        tr.step()
+    dt = (time.perf_counter() - t0) / n
+    return dict(ms_per_step=dt * 1e3, steps_per_s=1.0 / dt, steps_run=n, threads=torch.get_num_threads(),
+                vertices=int(w["verts"].shape[0]))
+
+
+def reference_workload_name(args):
+    """The reference arm runs the NAMED configuration when it fits the host (1 M vertices: ~3-4 s per step on 16 cores);
+    the 16 M-vertex torus needs > 120 GB of autograd state on the CPU, so there the 1 M torus is timed and
+    the line says so in config.workload / cpu_baseline.sample."""
+    kind, size, k = WORKLOADS[args.workload]
+    if kind == "torus" and size > 1024:
+        return "torus1m"
+    return args.workload
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    kind, size, k = WORKLOADS[args.workload]
-    full_n = 10 * size * size + 2 if kind == "icosphere" else size * size
-    sample = "icosphere100k" if kind == "icosphere" else "torus1m"
+    name = reference_workload_name(args)
+    kind, size, k = WORKLOADS[name]
+    w = build_host_workload(name)
     # torchrun pins OMP_NUM_THREADS=1; the reference arm is entitled to every host core
-    r = cpu_reference_steps_per_s(sample, full_n, max(1, min(args.steps, 3)), max(1, min(args.warmup, 1)),
-                                  threads=os.cpu_count())
-    sample_txt = ("oracle/step_port.py (torch-CPU port of the reference step) on %s = %d vertices, %.0f ms/step, "
-                  "scaled x%.2f to %d vertices" % (sample, r["sample_vertices"], r["sample_ms"],
-                                                  full_n / r["sample_vertices"], full_n))
+    r = time_oracle(w, args.steps, min(args.warmup, 1), threads=os.cpu_count(), budget_s=150.0)
+    sample_txt = ("oracle/step_port.py (torch-CPU port of the reference epoch body, src/multigrid_model.py:237-261) on the "
+                  "full %s workload (%d vertices, k = %d), %d timed steps of %.0f ms, wall clock, %d threads"
+                  % (name, r["vertices"], k, r["steps_run"], r["ms_per_step"], r["threads"]))
     line = {"impl": "reference", "metric": "train_steps_per_s", "value": r["steps_per_s"], "unit": "steps/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "vertices": full_n, "k": k, "hidden": HIDDEN},
+            "n_gpus": args.gpus, "steps": r["steps_run"], "steps_requested": args.steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "vertices": r["vertices"], "k": k, "hidden": HIDDEN},
             "cpu_baseline": {"value": r["steps_per_s"], "unit": "steps/s", "cores": r["threads"], "kind": "port",
                              "sample": sample_txt},
             "e2e": {"value": r["steps_per_s"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -181,22 +208,23 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ our arm
-def build_engine(args, dev, rank, world):
+def build_engine(args, dev, rank, world, workload=None):
     """Set-up (untimed): workload -> training-step engine.  Triangle meshes built on the host go through the
     reference-shaped API (MultigridGNN._normalize_eigenvectors / _build_features / _initialize_model / _make_engine);
     the torus grids are generated, assembled and sharded on the device (eigen-pinns_b200/workloads.py)."""
     import torch
-    kind, size, k = WORKLOADS[args.workload]
+    workload = workload or args.workload
+    kind, size, k = WORKLOADS[workload]
     if kind == "torus":
         eng, x_feats, adj, U_norm, n, nnz = pkg("workloads").build_torus_engine(size, k, dev, args.mlp_mode, HIDDEN,
                                                                                rank, world)
         return dict(engine=eng, n=n, k=k, nnz=nnz, lam_err=None, x_feats=x_feats, U_norm=U_norm, edge_index=None,
-                    adjacency=adj)
+                    adjacency=adj, host=None)
     if SRC not in sys.path:
         sys.path.insert(0, SRC)
     import config as cfg_mod
     import multigrid_model
-    w = build_host_workload(args.workload)
+    w = build_host_workload(workload)
     n = w["verts"].shape[0]
     cfg = cfg_mod.PINNConfig.from_yaml(os.path.join(SRC, "parameters.yml"))
     cfg.n_modes, cfg.mlp_mode, cfg.seed, cfg.hidden_layers = k, args.mlp_mode, 0, HIDDEN
@@ -223,42 +251,25 @@ def build_engine(args, dev, rank, world):
         nz = ref > 0
         lam_err = float(np.max(np.abs(np.sort(vals_rr)[nz] - ref[nz]) / ref[nz]))
     return dict(engine=eng, n=n, k=k, nnz=int(w["K"].nnz), lam_err=lam_err, x_feats=x_feats, U_norm=U_norm[0],
-                edge_index=edge_all, adjacency=None)
+                edge_index=edge_all, adjacency=None, host=w)
 
 
-def run_ours(args):
+def timed_steps(eng, args, dev, rank, world, epoch0, clock_sampler=None):
+    """Warm-up (eager, then phase timing, then CUDA-graph capture), then the timed region: K steps x R repeats with
+    R chosen so that the region lasts >= MIN_TIMED_MS.  The loss of every step is read back on the host with a delay
+    of one step (pinned ring), as the drop-in training loop does.  Returns a dict of measurements (ms = max over ranks)."""
     import torch
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists for the product path)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-    pkg().require_library()
-    cabi = pkg("_cabi")
-    wl = build_engine(args, dev, rank, world)
-    eng, n, k, nnz, lam_err = wl["engine"], wl["n"], wl["k"], wl["nnz"], wl["lam_err"]
-    x_feats, U_norm, edge_all, adj_dev = wl["x_feats"], [wl["U_norm"]], wl["edge_index"], wl["adjacency"]
-    device_built = adj_dev is not None
-    d_in = eng.h.shape[1]
-    flops_v = mlp_flops_per_vertex(d_in, HIDDEN, k)
-    epoch0 = 2500                                            # mid-ramp: correction scale 5.0, non-zero gradients
+    import torch.distributed as dist
+    cabi, engine_mod = pkg("_cabi"), pkg("engine")
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing.  Warm-up: W eager steps, a phase-timing pass (eager, events between phases),
-    # then the step is captured into one CUDA graph (two more untimed replays); the K timed steps replay it.
     for i in range(args.warmup):
         eng.step(epoch0 + i)
-    marks_all = []
-    n_phase = 5
+    marks_all, n_phase = [], 5
     for i in range(n_phase):
         marks = []
         eng.step(epoch0 + args.warmup + i, marks=marks)
@@ -277,66 +288,112 @@ def run_ours(args):
         except Exception as exc:                      # same kernels either way; only the launch mechanism differs
             sys.stderr.write("CUDA-graph capture failed (%r); timing eager launches instead\n" % (exc,))
             eng.enable_graph(False)
+    # estimate -> number of repeats
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
+    e0.record()
+    for i in range(3):
+        eng.step(epoch0 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    est = torch.tensor([e0.elapsed_time(e1) / 3.0], device=dev)
+    if world > 1:
+        dist.all_reduce(est, op=dist.ReduceOp.MAX)
+    repeats = max(1, int(np.ceil(MIN_TIMED_MS / (float(est.item()) * args.steps))))
+    n_timed = args.steps * repeats
+    reader = engine_mod.LossReader(depth=4)
+    if clock_sampler is not None:
+        clock_sampler.start()
     launches0 = cabi.launch_counter
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_start.record()
-    for i in range(args.steps):
-        eng.step(epoch0 + args.warmup + n_phase + 2 + i)
+    prev, loss_now = None, None
+    for i in range(n_timed):
+        ticket = reader.push(eng.step(epoch0 + 3 + i))
+        if prev is not None:
+            loss_now = reader.get(prev)               # loss of the previous step: the host stays one step ahead
+        prev = ticket
     t_end.record()
     barrier()
-    clk = clocks.stop() if rank == 0 else None
+    loss_now = reader.get(prev)
+    clk = clock_sampler.stop() if clock_sampler is not None else None
     launches = cabi.launch_counter - launches0
     if eng.use_graph and eng.launches_per_step:
-        launches = eng.launches_per_step * args.steps
+        launches = eng.launches_per_step * n_timed
     ms_total = t_start.elapsed_time(t_end)
     if world > 1:
         t = torch.tensor([ms_total], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    loss_now = float(eng.loss_acc.cpu().numpy()[5])
+    return dict(ms_step=ms_total / n_timed, n_timed=n_timed, repeats=repeats, phase=phase, clocks=clk,
+                launches=int(launches), loss=float(loss_now[5]), timed_ms=ms_total,
+                launches_by_entry=getattr(eng, "launches_by_entry", None))
 
-    # ---- SpMM alone (HBM roofline of the sparse operator)
-    pair = eng.pairs[-1]
-    s = eng._level_slices(len(eng.pairs) - 1)
-    ops = pkg("ops")
-    reps = 20
+
+def time_call(fn, reps_min=20):
+    """CUDA-event time of one call of fn (ms), repeated so that the timed region lasts >= 100 ms."""
+    import torch
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ops.spmm2(pair, eng.U_pred[s], out_K=eng.KU[s], out_M=eng.MU[s])
+    fn()
     torch.cuda.synchronize()
     e0.record()
-    for _ in range(reps):
-        ops.spmm2(pair, eng.U_pred[s], out_K=eng.KU[s], out_M=eng.MU[s])
+    for _ in range(3):
+        fn()
     e1.record()
     torch.cuda.synchronize()
-    spmm_ms = e0.elapsed_time(e1) / reps
+    reps = max(reps_min, int(100.0 / max(e0.elapsed_time(e1) / 3.0, 1e-3)))
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def run_ours(args):
+    import ctypes
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    pkg().require_library()
+    cabi, ops = pkg("_cabi"), pkg("ops")
+    wl = build_engine(args, dev, rank, world)
+    eng, n, k, nnz, lam_err = wl["engine"], wl["n"], wl["k"], wl["nnz"], wl["lam_err"]
+    x_feats, U_norm, edge_all, adj_dev = wl["x_feats"], [wl["U_norm"]], wl["edge_index"], wl["adjacency"]
+    device_built = adj_dev is not None
+    d_in = eng.h.shape[1]
+    flops_v = mlp_flops_per_vertex(d_in, HIDDEN, k)
+    epoch0 = 2500                                            # mid-ramp: correction scale 5.0, non-zero gradients
+    peaks = measured_peaks()
+
+    m = timed_steps(eng, args, dev, rank, world, epoch0, ClockSampler(local_rank) if rank == 0 else None)
+    ms_step, phase = m["ms_step"], m["phase"]
+
+    # ---- kernels timed alone (burst peaks apply): dual SpMM, forward chain of the MLP
+    pair = eng.pairs[-1]
+    s = eng._level_slices(len(eng.pairs) - 1)
+    spmm_ms = time_call(lambda: ops.spmm2(pair, eng.U_pred[s], out_K=eng.KU[s], out_M=eng.MU[s]))
     n_loc = pair.n
     spmm_bytes = 12 * pair.K.nnz + 4 * (n_loc + 1) + 12 * n_loc * k
-    peaks = measured_peaks()
-    # ---- dominant kernel alone: one hidden layer of the tensor-core MLP (same kernel serves forward and dX)
-    hidden_ms, hidden_bytes = None, 0
-    if args.mlp_mode == "bf16":
-        import ctypes
-        m = eng.mlp
-        P = lambda t: ctypes.c_void_p(t.data_ptr())
-        st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        run = lambda: cabi.call("ep_tc_linear_fwd_bf16", m.n, m.pd[1], m.dims[2], m.pd[2], P(m.acts[0]), P(m.Wp[1]),
-                                P(m.p.b[1]), 1, P(m.acts[1]), P(m.masks[1]), st())
-        run()
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(reps):
-            run()
-        e1.record()
-        torch.cuda.synchronize()
-        hidden_ms = e0.elapsed_time(e1) / reps
-        n_pad = (m.n + 127) // 128 * 128
-        hidden_bytes = n_pad * (m.pd[1] + m.pd[2]) * 2 + n_pad * (m.pd[2] // 8)
+    chain_ms, chain_bytes, chain_flops = None, 0, 0
+    if args.mlp_mode == "bf16" and getattr(eng.mlp, "chain_fwd", False):
+        mm = eng.mlp
+        chain_ms = time_call(lambda: mm.forward(eng.h, U_base=eng.U_base, scale=5.0, U_pred=eng.U_pred))
+        pw_ms = time_call(mm._pack_weights)                 # forward() re-packs the weights first: subtract that launch group
+        chain_ms -= pw_ms
+        n_rows = mm.n
+        # algorithmic bytes: packed input read, every hidden activation + ReLU mask written once, U_base read, U_pred written
+        chain_bytes = n_rows * (2 * mm.pd[0] + sum(2 * w + w // 8 for w in mm.pd[1:-1]) + 8 * k)
+        chain_flops = 2.0 * n_rows * sum(mm.dims[i] * mm.dims[i + 1] for i in range(mm.L))
 
     # ---- samplers at BASELINE config 3 size (1 M-point cloud): FPS iterations and one voxel hierarchy
     samplers_info = None
@@ -382,18 +439,53 @@ def run_ours(args):
             prev = cur
         pipe.result(prev)
         torch.cuda.synchronize()
+        n_e2e = max(args.steps, int(np.ceil(MIN_TIMED_MS / max(ms_step * 1.5, 1e-3))))
         t0 = time.perf_counter()
         prev = pipe.submit(x_host, ub_host, epoch0)
         e2e_loss = None
-        for i in range(1, args.steps + 1):
-            cur = pipe.submit(x_host, ub_host, epoch0 + i) if i < args.steps else None
+        for i in range(1, n_e2e + 1):
+            cur = pipe.submit(x_host, ub_host, epoch0 + i) if i < n_e2e else None
             e2e_loss = pipe.result(prev)
             prev = cur
-        dt = (time.perf_counter() - t0) / args.steps
+        dt = (time.perf_counter() - t0) / n_e2e
         e2e = {"value": 1.0 / dt, "unit": "steps/s", "h2d_bytes_per_step": int(pipe.h2d_bytes),
-               "d2h_bytes_per_step": int(pipe.d2h_bytes), "ms_per_step": dt * 1e3,
-               "api": "engine.HostFedPipeline.submit/result (x_feats + U_base uploaded every step, loss read back)",
+               "d2h_bytes_per_step": int(pipe.d2h_bytes), "ms_per_step": dt * 1e3, "steps_timed": n_e2e,
+               "api": "engine.HostFedPipeline.submit/result (x_feats + U_base uploaded from pinned host memory every "
+                      "step, aggregation + packing on the device, six loss terms read back)",
                "loss": float(e2e_loss[5])}
+        del pipe, x_host, ub_host
+
+    # ---- CPU baseline beside it: the oracle on the SAME workload (bounded: 1 warm-up + 3 timed steps), rank 0, N = 1
+    cpu = None
+    if not args.no_cpu_baseline and world == 1 and rank == 0:
+        host = wl["host"] if wl["host"] is not None else build_host_workload(reference_workload_name(args))
+        r = time_oracle(host, 3, 1, threads=os.cpu_count())
+        cpu = {"value": r["steps_per_s"], "unit": "steps/s", "cores": r["threads"], "kind": "port",
+               "sample": "oracle/step_port.py on the %s workload (%d vertices), 3 timed steps of %.0f ms after 1 warm-up, "
+                         "wall clock" % (args.workload if wl["host"] is not None else reference_workload_name(args),
+                                         r["vertices"], r["ms_per_step"])}
+
+    # ---- BASELINE config 5 (north star): 16 M-vertex torus, k = 64, same engine, same number of GPUs
+    torus = None
+    if not args.no_torus and args.workload != "torus16m":
+        del eng, wl, x_feats, U_norm, m["phase"]
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        try:
+            twl = build_engine(args, dev, rank, world, workload="torus16m")
+            targs = argparse.Namespace(**vars(args))
+            targs.steps, targs.warmup = max(3, min(args.steps, 10)), 3
+            tm = timed_steps(twl["engine"], targs, dev, rank, world, epoch0)
+            torus = {"workload": "torus16m", "vertices": twl["n"], "k": twl["k"], "ms_per_step": tm["ms_step"],
+                     "steps_per_s": 1000.0 / tm["ms_step"], "timed_steps": tm["n_timed"], "phase_ms": tm["phase"],
+                     "loss": tm["loss"], "n_gpus": world, "scaling": "strong",
+                     "mlp_tflops": mlp_flops_per_vertex(twl["engine"].h.shape[1], HIDDEN, twl["k"]) * twl["n"] / world /
+                                   ((tm["phase"].get("mlp_fwd", 0) + tm["phase"].get("mlp_bwd", 0)) * 1e-3) / 1e12}
+            del twl
+        except Exception as exc:                                   # e.g. not enough memory: say so, keep the headline
+            torus = {"workload": "torus16m", "error": repr(exc)[:300]}
+    ms_phase = phase
 
     def finish():
         """Multi-rank exit: tearing the NCCL communicator down while captured graphs still reference it can block
@@ -408,51 +500,58 @@ def run_ours(args):
     if rank != 0:
         finish()
         return
-    mlp_ms = phase.get("mlp_fwd", 0.0) + phase.get("mlp_bwd", 0.0)
+    mlp_ms = ms_phase.get("mlp_fwd", 0.0) + ms_phase.get("mlp_bwd", 0.0)
     n_global = n
     tflops = flops_v * n_global / world / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
-    tensor_peak = peaks["bf16_sustained"]
-    mlp_roof = {"bound": "tensor", "kernel": "corrector MLP forward+backward, all layers (%s)" % args.mlp_mode,
-                "achieved": tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tflops / tensor_peak,
-                "peak_source": peaks["source"] + " bf16 sustained", "ms_per_step": mlp_ms, "flop_per_vertex": flops_v,
-                "note": "each layer kernel is HBM-bound (AI 128 flop/B < ridge); see roofline for the dominant kernel"}
-    if hidden_ms is not None:
-        gbs = hidden_bytes / (hidden_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "tc_linear_kernel<HIDDEN> (tcgen05, one 256->256 layer: relu(A W^T + b) -> packed bf16 + mask)",
+    eager_ms = sum(ms_phase.values())
+    shares = {p: v / eager_ms for p, v in ms_phase.items()} if eager_ms > 0 else {}
+    mlp_roof = {"bound": "tensor", "kernel": "corrector MLP forward + backward, all layers (%s)" % args.mlp_mode,
+                "achieved": tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": tflops / peaks["bf16_sustained"], "frac_of_burst_peak": tflops / peaks["bf16_burst"],
+                "peak_source": peaks["source"] + " bf16 sustained (kernels timed inside the >= 1 s step loop)",
+                "ms_per_step": mlp_ms, "flop_per_vertex": flops_v, "share_of_step": shares.get("mlp_fwd", 0) + shares.get("mlp_bwd", 0)}
+    if chain_ms is not None:
+        gbs = chain_bytes / (chain_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm",
+                    "kernel": "tc_chain_kernel<FWD> (tcgen05: all %d layers of the corrector for a pair of 128-vertex tiles per "
+                              "persistent CTA; activations + ReLU masks streamed to HBM once, never read back)" % eng_layers(d_in, k),
                     "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
-                    "traffic": NCU_TRAFFIC_HIDDEN_PER_VERTEX * n_loc if n_loc else None,
-                    "peak_source": peaks["source"] + " hbm copy", "ms": hidden_ms, "bytes_per_launch": hidden_bytes,
-                    "launches_per_step": 12, "share_of_step": 12 * hidden_ms / ms_step,
-                    "tflops_this_kernel": 2.0 * n_loc * 256 * 256 / (hidden_ms * 1e-3) / 1e12}
+                    "traffic": NCU_TRAFFIC_CHAIN_FWD_PER_VERTEX * n_loc,
+                    "peak_source": peaks["source"] + " hbm copy (kernel timed alone)", "ms": chain_ms,
+                    "bytes_per_launch": chain_bytes, "launches_per_step": 1, "share_of_step": chain_ms / ms_step,
+                    "arithmetic_intensity_flop_per_byte": chain_flops / chain_bytes,
+                    "tflops_this_kernel": chain_flops / (chain_ms * 1e-3) / 1e12,
+                    "frac_of_tensor_burst_peak": chain_flops / (chain_ms * 1e-3) / 1e12 / peaks["bf16_burst"],
+                    "why_hbm": "AI = %.0f flop/B is below the ridge %.0f flop/B of the measured peaks"
+                               % (chain_flops / chain_bytes, peaks["bf16_burst"] * 1e3 / peaks["hbm"])}
     else:
         roofline = dict(mlp_roof, traffic=None)
     spmm_gbs = spmm_bytes / (spmm_ms * 1e-3) / 1e9
     spmm_roof = {"bound": "hbm", "kernel": "ep_spmm2_csr_f32 (K U and M U, shared pattern)", "achieved": spmm_gbs,
                  "peak": peaks["hbm"], "unit": "GB/s", "frac": spmm_gbs / peaks["hbm"], "ms": spmm_ms,
-                 "bytes_per_launch": spmm_bytes, "traffic": None}
-    cpu = None
-    if not args.no_cpu_baseline and world == 1:
-        kind, size, _ = WORKLOADS[args.workload]
-        sample = "icosphere100k" if kind == "icosphere" else "torus1m"
-        if n_global < 150000:
-            sample = args.workload
-        r = cpu_reference_steps_per_s(sample, n_global, 2, 1, threads=os.cpu_count())
-        cpu = {"value": r["steps_per_s"], "unit": "steps/s", "cores": r["threads"], "kind": "port",
-               "sample": "oracle/step_port.py on %s (%d vertices, %.0f ms/step) scaled to %d vertices"
-                         % (sample, r["sample_vertices"], r["sample_ms"], n_global)}
+                 "bytes_per_launch": spmm_bytes, "traffic": NCU_TRAFFIC_SPMM2_PER_VERTEX * n_loc,
+                 "share_of_step": spmm_ms / ms_step}
     line = {"metric": "train_steps_per_s", "value": 1000.0 / ms_step, "unit": "steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32" if args.mlp_mode == "fp32" else "bf16",
             "data": "synthetic",
             "config": {"workload": args.workload, "vertices": n_global, "k": k, "hidden": HIDDEN, "mlp_in": d_in,
                        "nnz_per_operator": int(nnz), "mlp_mode": args.mlp_mode, "levels": 1,
-                       "parallelism": "vertex-shard x%d" % world, "cuda_graph": bool(eng.use_graph),
-                       "l2": "inputs larger than L2 (U, KU, MU, activations >> 126 MB)"},
-            "clocks": clk, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "mlp_roofline": mlp_roof,
-            "spmm_roofline": spmm_roof, "cpu_baseline": cpu,
-            "samplers": samplers_info, "phase_ms": phase, "host_issue_ms": host_issue_ms, "loss": loss_now, "lambda_rel_err_rayleigh_ritz": lam_err}
+                       "parallelism": "vertex-shard x%d" % world, "cuda_graph": bool(args.no_graph is False),
+                       "l2": "inputs larger than L2 (U, KU, MU, activations >> 126 MB)",
+                       "timed_region": "%d steps x %d repeats = %d steps, %.0f ms; loss read back every step with a "
+                                       "delay of one step" % (args.steps, m["repeats"], m["n_timed"], m["timed_ms"])},
+            "timed_steps": m["n_timed"], "clocks": m["clocks"], "gpu_launches": m["launches"],
+            "launches_per_step_by_entry": m["launches_by_entry"], "e2e": e2e, "roofline": roofline,
+            "mlp_roofline": mlp_roof, "spmm_roofline": spmm_roof, "cpu_baseline": cpu, "samplers": samplers_info,
+            "phase_ms": ms_phase, "phase_share_of_eager_step": shares, "host_issue_ms": host_issue_ms,
+            "loss": m["loss"], "lambda_rel_err_rayleigh_ritz": lam_err, "north_star_torus16m": torus}
     print(json.dumps(line))
     finish()
+
+
+def eng_layers(d_in, k):
+    return len(HIDDEN) + 1
 
 
 def main():
@@ -465,6 +564,7 @@ def main():
     ap.add_argument("--mlp-mode", default=os.environ.get("EP_MLP_MODE", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-samplers", action="store_true")
+    ap.add_argument("--no-torus", action="store_true", help="skip the 16 M-vertex torus block (BASELINE config 5)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

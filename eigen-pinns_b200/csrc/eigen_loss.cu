@@ -416,7 +416,7 @@ eigen_bwd_prepare_kernel(int n, int k, const float* __restrict__ U, int ldu, con
 // MU values from the other lanes with shuffles and S from shared memory.
 template <int KVT>     // KVT = k / 4 when instantiated for a fixed width (fully unrolled product), 0 = generic
 __global__ void __launch_bounds__(256)
-eigen_bwd_fused_sym_kernel(int n, int k, int lpr_shift, const int32_t* __restrict__ rowptr,
+eigen_bwd_fused_sym_kernel(int row0, int n, int k, int lpr_shift, const int32_t* __restrict__ rowptr,
                            const int32_t* __restrict__ col, const float* __restrict__ valK,
                            const float* __restrict__ valM, const float* __restrict__ KU,
                            const float* __restrict__ MU, int ld, const float* __restrict__ coef, float out_scale_v,
@@ -448,9 +448,10 @@ eigen_bwd_fused_sym_kernel(int n, int k, int lpr_shift, const int32_t* __restric
   const float4 lam4 = *reinterpret_cast<const float4*>(s_lam + cofs);
   const float4 a24 = *reinterpret_cast<const float4*>(s_a2 + cofs);
   const long long groups_per_grid = ((long long)gridDim.x * blockDim.x) >> lpr_shift;
-  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> lpr_shift;
-       row < (long long)((n + groups_per_grid - 1) / groups_per_grid) * groups_per_grid; row += groups_per_grid) {
-    const bool valid = row < n;
+  for (long long ri = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> lpr_shift;
+       ri < (long long)((n + groups_per_grid - 1) / groups_per_grid) * groups_per_grid; ri += groups_per_grid) {
+    const bool valid = ri < n;
+    const long long row = row0 + ri;               // output rows [row0, row0 + n)
     const int start = valid ? __ldg(rowptr + row) : 0;
     const int end = valid ? __ldg(rowptr + row + 1) : 0;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -518,7 +519,7 @@ eigen_bwd_fused_sym_kernel(int n, int k, int lpr_shift, const int32_t* __restric
 // warp are broadcast from shared memory (8 LDS.128 per row instead of 32 per lane-row), then the result returns to
 // the float4 layout through shared memory for the coalesced store.
 __global__ void __launch_bounds__(256)
-eigen_bwd_fused_sym_k32_kernel(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+eigen_bwd_fused_sym_k32_kernel(int row0, int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                const float* __restrict__ valK, const float* __restrict__ valM,
                                const float* __restrict__ KU, const float* __restrict__ MU, int ld,
                                const float* __restrict__ coef, float out_scale_v,
@@ -549,8 +550,9 @@ eigen_bwd_fused_sym_k32_kernel(int n, const int32_t* __restrict__ rowptr, const 
   const long long rows_per_grid = (long long)gridDim.x * 32;                  // 8 warps x 4 rows per CTA
   const long long n_iter = ((long long)n + rows_per_grid - 1) / rows_per_grid;
   for (long long it = 0; it < n_iter; ++it) {
-    const long long row = it * rows_per_grid + (long long)blockIdx.x * 32 + warp * 4 + rsub;
-    const bool valid = row < n;
+    const long long ri = it * rows_per_grid + (long long)blockIdx.x * 32 + warp * 4 + rsub;
+    const bool valid = ri < n;
+    const long long row = row0 + ri;
     const int start = valid ? __ldg(rowptr + row) : 0;
     const int end = valid ? __ldg(rowptr + row + 1) : 0;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -725,12 +727,20 @@ int ep_eigen_bwd_prepare_f32(int n, int k, const float* U, int ldu, const float*
 int ep_eigen_bwd_fused_sym_f32(int n, int k, const int32_t* rowptr, const int32_t* col, const float* valK,
                                const float* valM, const float* KU, const float* MU, int ld, const float* coef,
                                float out_scale, const float* out_scale_dev, float* dU, int ldo, ep_stream_t stream) {
-  EP_REQUIRE(n >= 0 && k > 0, "bad size");
+  return ep_eigen_bwd_fused_sym_rows_f32(0, n, k, rowptr, col, valK, valM, KU, MU, ld, coef, out_scale, out_scale_dev,
+                                         dU, ldo, stream);
+}
+
+int ep_eigen_bwd_fused_sym_rows_f32(int row0, int n, int k, const int32_t* rowptr, const int32_t* col,
+                                    const float* valK, const float* valM, const float* KU, const float* MU, int ld,
+                                    const float* coef, float out_scale, const float* out_scale_dev, float* dU, int ldo,
+                                    ep_stream_t stream) {
+  EP_REQUIRE(n >= 0 && k > 0 && row0 >= 0, "bad size");
   if (n == 0) return EP_OK;
   EP_REQUIRE(rowptr && col && valK && valM && KU && MU && coef && dU, "null pointer");
   if (k % 4 != 0 || k > 128 || ld % 4 != 0 || ldo % 4 != 0 || !ep::aligned16(KU) || !ep::aligned16(MU) ||
       !ep::aligned16(dU)) {
-    ep::set_error("ep_eigen_bwd_fused_sym_f32: needs k %% 4 == 0, k <= 128 and 16-byte aligned rows");
+    ep::set_error("ep_eigen_bwd_fused_sym_rows_f32: needs k %% 4 == 0, k <= 128 and 16-byte aligned rows");
     return EP_ERR_UNSUPPORTED;
   }
   const int kv = k / 4;
@@ -752,13 +762,13 @@ int ep_eigen_bwd_fused_sym_f32(int n, int k, const int32_t* rowptr, const int32_
     long long g32 = ((long long)n + 31) / 32;
     const long long cap32 = (long long)ep::sm_count() * 8;
     if (g32 > cap32) g32 = cap32;
-    eigen_bwd_fused_sym_k32_kernel<<<(unsigned)g32, 256, 0, st>>>(n, rowptr, col, valK, valM, KU, MU, ld, coef,
+    eigen_bwd_fused_sym_k32_kernel<<<(unsigned)g32, 256, 0, st>>>(row0, n, rowptr, col, valK, valM, KU, MU, ld, coef,
                                                                   out_scale, out_scale_dev, dU, ldo);
     EP_LAUNCH_CHECK("eigen_bwd_fused_sym_k32_kernel");
     return EP_OK;
   }
 #define EP_FUSED_LAUNCH(KVT) eigen_bwd_fused_sym_kernel<KVT><<<(unsigned)grid, 256, smem, st>>>( \
-      n, k, lpr_shift, rowptr, col, valK, valM, KU, MU, ld, coef, out_scale, out_scale_dev, dU, ldo)
+      row0, n, k, lpr_shift, rowptr, col, valK, valM, KU, MU, ld, coef, out_scale, out_scale_dev, dU, ldo)
   switch (kv) {
     case 4: EP_FUSED_LAUNCH(4); break;
     case 8: EP_FUSED_LAUNCH(8); break;

@@ -34,6 +34,13 @@ class HaloExchanger:
 
     def exchange(self, rows, n_own):
         """rows: (n_own + n_halo) x k tensor; fills rows[n_own:] from the owners."""
+        for w in self.start(rows, n_own):
+            w.wait()
+        return rows
+
+    def start(self, rows, n_own):
+        """Enqueue the exchange and return the pending work objects: kernels launched on the current stream before
+        `wait()` is called on them overlap the transfer (NCCL point-to-point runs on the communicator's own stream)."""
         reqs, keep = [], []
         for p, idx in self.send_idx.items():
             key = (p, rows.shape[1])
@@ -44,10 +51,8 @@ class HaloExchanger:
             reqs.append(dist.P2POp(dist.isend, buf, p, self.group))
         for p, (off, cnt) in self.recv.items():
             reqs.append(dist.P2POp(dist.irecv, rows[n_own + off:n_own + off + cnt], p, self.group))
-        if reqs:
-            for w in dist.batch_isend_irecv(reqs):
-                w.wait()
-        return rows
+        self._keep = keep
+        return dist.batch_isend_irecv(reqs) if reqs else []
 
 
 def resolve_send_lists(plan: LevelPlan, group=None):
@@ -80,7 +85,13 @@ class ShardedTrainStepEngine(TrainStepEngine):
         assert off == h_local.shape[0] == U_base_local.shape[0]
         super().__init__(h_local, U_base_local, pairs, offsets, params, cfg, lam_target, mlp_mode)
         self.halo = [HaloExchanger(pl, dev, lambda rows, idx, out: ops.gather_rows(rows, idx, out=out), group) for pl in plans]
+        self.overlap = True                     # interior rows while the halo is in flight
         self.dCorr.zero_()                      # halo rows never receive a gradient on this rank
+
+    def _mlp_rows(self):
+        # single level: rows are [owned | halo], and the corrector is only needed on the owned ones (the halo rows
+        # of U_pred arrive through the exchange).  Stacked levels interleave owned and halo blocks: evaluate all.
+        return self.plans[0].n_own if len(self.plans) == 1 else self.n_total
 
     def _ext(self, buf, li):
         pl = self.plans[li]
@@ -97,15 +108,42 @@ class ShardedTrainStepEngine(TrainStepEngine):
         dist.all_reduce(self.params.grad, group=self.group)
 
     def loss_forward(self):
-        for li, pl in enumerate(self.plans):
-            self.halo[li].exchange(self._ext(self.U_pred, li), pl.n_own)
-        super().loss_forward()
+        """Per level: start the halo exchange of U_pred, apply K and M to the interior rows meanwhile, wait, apply them
+        to the boundary rows; then partials -> all-reduce -> finalize exactly as on one GPU."""
+        c = self.cfg
+        for li, (pl, pair) in enumerate(zip(self.plans, self.pairs)):
+            s = self._level_slices(li)
+            U_ext = self._ext(self.U_pred, li)
+            pending = self.halo[li].start(U_ext, pl.n_own)
+            a, b = pl.interior if self.overlap else (0, 0)
+            ops.spmm2(pair, U_ext, out_K=self.KU[s], out_M=self.MU[s], rows=(a, b))
+            for w in pending:
+                w.wait()
+            ops.spmm2(pair, U_ext, out_K=self.KU[s], out_M=self.MU[s], rows=(0, a))
+            ops.spmm2(pair, U_ext, out_K=self.KU[s], out_M=self.MU[s], rows=(b, pl.n_own))
+            ops.eigen_partials(self.U_pred[s], self.KU[s], self.MU[s], out=self.partials[li])
+            self._reduce_partials(li)
+            ops.eigen_finalize(self.k, self._n_global(li), self.partials[li], c.w_res, c.w_orth, self.loss_acc,
+                               coef=self.coefs[li], lam_out=self.lams[li], level0=(li == 0),
+                               lam_target=self.lam_target, w_trace=c.w_trace, w_order=c.w_order, w_eigen=c.w_eigen,
+                               overwrite=(li == 0))
 
     def loss_backward(self, scale, scale_dev=None):
-        for li, pl in enumerate(self.plans):
-            self.halo[li].exchange(self._ext(self.KU, li), pl.n_own)
-            self.halo[li].exchange(self._ext(self.MU, li), pl.n_own)
-        super().loss_backward(scale, scale_dev=scale_dev)
+        """K U and M U live side by side in one row (engine.KUMU), so their halo rows travel as ONE message; the
+        gradient of the interior rows is computed while it is in flight."""
+        for li, (pl, pair) in enumerate(zip(self.plans, self.pairs)):
+            s = self._level_slices(li)
+            if not ops.eigen_bwd_fused_ok(pair, self.k, self.KU[s], self.MU[s], self.dCorr[s]):
+                raise NotImplementedError("the vertex-sharded backward uses the fused symmetric kernel: k must be a "
+                                          "multiple of 4 (<= 128)")
+            pending = self.halo[li].start(self._ext(self.KUMU, li), pl.n_own)
+            a, b = pl.interior if self.overlap else (0, 0)
+            args = (pair, self.KU[s], self.MU[s], self.coefs[li], scale, self.dCorr[s], scale_dev)
+            ops.eigen_bwd_fused(*args, rows=(a, b))
+            for w in pending:
+                w.wait()
+            ops.eigen_bwd_fused(*args, rows=(0, a))
+            ops.eigen_bwd_fused(*args, rows=(b, pl.n_own))
 
 
 def shard_rows(global_rows, plans, global_offsets):

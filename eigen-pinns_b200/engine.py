@@ -111,8 +111,10 @@ class TrainStepEngine:
         k = self.k
         f32 = dict(dtype=torch.float32, device=self.dev)
         self.U_pred = torch.empty((self.n_total, k), **f32)
-        self.KU = torch.empty((self.n_total, k), **f32)
-        self.MU = torch.empty((self.n_total, k), **f32)
+        # K U and M U of a vertex sit side by side in one row of width 2k: the backward gather reads both with one
+        # 8k-byte access per neighbour, and the vertex-sharded engine exchanges their halo rows as ONE message
+        self.KUMU = torch.empty((self.n_total, 2 * k), **f32)
+        self.KU, self.MU = self.KUMU[:, :k], self.KUMU[:, k:]
         self._bwd_scratch = None       # KU_bar, MU_bar, D: only the unfused (non-symmetric) backward needs them
         self.dCorr = torch.empty((self.n_total, k), **f32)
         ws = ops.EigenWorkspace.get(k, self.dev)
@@ -122,11 +124,12 @@ class TrainStepEngine:
         self.loss_acc = torch.zeros(6, dtype=torch.float64, device=self.dev)
         self.lam_target = lam_target.to(**f32).contiguous() if lam_target is not None else None
         self.mlp_mode = mlp_mode
+        self.n_mlp = self._mlp_rows()                  # rows the corrector is evaluated on (all, unless sharded)
         if mlp_mode == "fp32":
-            self.mlp = Fp32Mlp(self.n_total, params, self.dev)
+            self.mlp = Fp32Mlp(self.n_mlp, params, self.dev)
         elif mlp_mode == "bf16":
             from .mlp_tc import TcMlp
-            self.mlp = TcMlp(self.n_total, params, self.dev, h)
+            self.mlp = TcMlp(self.n_mlp, params, self.dev, h[:self.n_mlp])
             self.mlp.want_corr = False
         else:
             raise ValueError("mlp_mode must be 'fp32' or 'bf16'")
@@ -139,7 +142,13 @@ class TrainStepEngine:
         return self.cfg.corr_scale * min(1.0, epoch / self.cfg.ramp_epochs)
 
     def forward(self, scale, scale_dev=None):
-        return self.mlp.forward(self.h, U_base=self.U_base, scale=scale, U_pred=self.U_pred, scale_dev=scale_dev)
+        m = self.n_mlp
+        return self.mlp.forward(self.h[:m], U_base=self.U_base[:m], scale=scale, U_pred=self.U_pred[:m],
+                                scale_dev=scale_dev)
+
+    def mlp_backward(self):
+        m = self.n_mlp
+        self.mlp.backward(self.h[:m], self.dCorr[:m])
 
     def _level_slices(self, li):
         off, n = self.offsets[li], self.pairs[li].n
@@ -179,6 +188,9 @@ class TrainStepEngine:
                            max(p.step_count, 1), c.grad_clip, p.sq_norm, hyper_dev)
 
     # hooks for the vertex-sharded engine
+    def _mlp_rows(self):
+        return self.n_total
+
     def _n_global(self, li):
         return self.pairs[li].n
 
@@ -208,7 +220,7 @@ class TrainStepEngine:
         mark("loss_fwd")
         self.loss_backward(scale)
         mark("loss_bwd")
-        self.mlp.backward(self.h, self.dCorr)
+        self.mlp_backward()
         mark("mlp_bwd")
         self.optimizer_step(self.cfg.lr if lr is None else lr)
         mark("optim")
@@ -233,7 +245,7 @@ class TrainStepEngine:
         self.forward(0.0, scale_dev=sd)
         self.loss_forward()
         self.loss_backward(0.0, scale_dev=sd)
-        self.mlp.backward(self.h, self.dCorr)
+        self.mlp_backward()
         self.optimizer_step(0.0, hyper_dev=self.hyper[1:3])
 
     def _step_graph(self, epoch, lr):
@@ -246,11 +258,13 @@ class TrainStepEngine:
         if self._graph is None:
             from . import _cabi
             torch.cuda.synchronize()
-            before = _cabi.launch_counter
+            before, by0 = _cabi.launch_counter, dict(_cabi.launch_by_entry)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._step_body_dev()
             self.launches_per_step = _cabi.launch_counter - before
+            self.launches_by_entry = {k_: v - by0.get(k_, 0) for k_, v in _cabi.launch_by_entry.items()
+                                      if v - by0.get(k_, 0) > 0}
             self._graph = g
             self._captured_ptrs = self._io_ptrs()
         elif self._io_ptrs() != self._captured_ptrs:
@@ -274,7 +288,7 @@ class TrainStepEngine:
         self.h.copy_(h_host, non_blocking=True)
         self.U_base.copy_(U_base_host, non_blocking=True)
         if hasattr(self.mlp, "input_changed"):
-            self.mlp.input_changed(self.h)
+            self.mlp.input_changed(self.h[:self.n_mlp])
         return self.step(epoch, lr).cpu().numpy()
 
 
@@ -340,7 +354,7 @@ class HostFedPipeline:
         main.wait_event(self.uploaded[s])
         self.aggregate(self.x_dev[s], self.e.h)
         if hasattr(self.e.mlp, "input_changed"):
-            self.e.mlp.input_changed(self.e.h)
+            self.e.mlp.input_changed(self.e.h[:self.e.n_mlp])
         # the engine (and a captured CUDA graph of its step) reads U_base at a FIXED address: copy, never rebind
         self.e.U_base.copy_(self.u_dev[s], non_blocking=True)
         acc = self.e.step(epoch, lr)

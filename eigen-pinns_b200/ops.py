@@ -47,16 +47,27 @@ def spmm(A: CsrMatrix, X, out=None):
     return Y
 
 
-def spmm2(pair: OperatorPair, X, out_K=None, out_M=None):
-    """(K X, M X) with one pass over the shared sparsity pattern."""
+def _off(t, elements):
+    """Device pointer `elements` items into tensor t."""
+    return ctypes.c_void_p(t.data_ptr() + elements * t.element_size())
+
+
+def spmm2(pair: OperatorPair, X, out_K=None, out_M=None, rows=None):
+    """(K X, M X) with one pass over the shared sparsity pattern.  rows=(a, b) restricts the product to that row
+    range (outputs are still indexed by the full row number): the sharded engine computes interior rows while
+    the halo exchange is in flight, then the boundary rows."""
     X = _check(_rowmajor(X))
     k = X.shape[1]
     n = pair.n
     KU = out_K if out_K is not None else torch.empty((n, k), device=X.device, dtype=torch.float32)
     MU = out_M if out_M is not None else torch.empty((n, k), device=X.device, dtype=torch.float32)
     assert KU.stride(0) == MU.stride(0)
-    call("ep_spmm2_csr_f32", n, k, _ptr(pair.K.rowptr), _ptr(pair.K.col), _ptr(pair.K.val), _ptr(pair.M.val),
-         _ptr(X), X.stride(0), _ptr(KU), _ptr(MU), KU.stride(0), _stream())
+    a, b = (0, n) if rows is None else rows
+    if b <= a:
+        return KU, MU
+    ld = KU.stride(0)
+    call("ep_spmm2_csr_f32", b - a, k, _off(pair.K.rowptr, a), _ptr(pair.K.col), _ptr(pair.K.val), _ptr(pair.M.val),
+         _ptr(X), X.stride(0), _off(KU, a * ld), _off(MU, a * ld), ld, _stream())
     return KU, MU
 
 
@@ -171,13 +182,21 @@ def eigen_bwd_fused_ok(pair, k, *tensors):
             and all(t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in tensors))
 
 
-def eigen_bwd_fused(pair, KU, MU, coef, scale, out, scale_dev=None):
-    """dL/dU for symmetric (K, M) in one gather pass (see ep_eigen_bwd_fused_sym_f32)."""
-    n, k = KU.shape
+def eigen_bwd_fused(pair, KU, MU, coef, scale, out, scale_dev=None, rows=None):
+    """dL/dU for symmetric (K, M) in one gather pass (see ep_eigen_bwd_fused_sym_f32).  KU / MU hold every row the
+    pattern references (owned and halo); rows=(a, b) restricts the OUTPUT rows (interior / boundary split)."""
+    k = KU.shape[1]
+    n = out.shape[0]
     assert KU.stride(0) == MU.stride(0)
-    call("ep_eigen_bwd_fused_sym_f32", n, k, _ptr(pair.K.rowptr), _ptr(pair.K.col), _ptr(pair.K.val), _ptr(pair.M.val),
-         _ptr(KU), _ptr(MU), KU.stride(0), _ptr(coef), float(scale), _ptr(scale_dev), _ptr(out), out.stride(0),
-         _stream())
+    a, b = (0, n) if rows is None else rows
+    if b <= a:
+        return out
+    # the kernel reads row i of KU / MU for output row i: shift those base pointers together with the output;
+    # gathered neighbours are addressed from the unshifted bases through absolute column indices, so the shifted
+    # call passes the column-relative bases explicitly (gather base = row 0)
+    call("ep_eigen_bwd_fused_sym_rows_f32", a, b - a, k, _ptr(pair.K.rowptr), _ptr(pair.K.col), _ptr(pair.K.val),
+         _ptr(pair.M.val), _ptr(KU), _ptr(MU), KU.stride(0), _ptr(coef), float(scale), _ptr(scale_dev), _ptr(out),
+         out.stride(0), _stream())
     return out
 
 

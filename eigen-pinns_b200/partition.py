@@ -1,13 +1,46 @@
 """Vertex sharding and halo plans for the multi-GPU training step (host logic, numpy only).
 
-Each resolution level is cut into contiguous vertex ranges, one per rank (the meshes are ordered
-for locality, so contiguous ranges have small boundaries).  A rank owns the rows of K, M, U and of
+Each resolution level is cut into contiguous vertex ranges, one per rank.  Contiguous ranges only have
+small boundaries when the vertex order is local: structured grids are (row-major slabs), arbitrary meshes
+should be permuted first (`z_order` + `permute_mesh`: latitude bands, two neighbours per rank).  A rank owns the rows of K, M, U and of
 the corrector input in its range; to apply K and M it also needs the rows of U that its columns
 reference outside the range - the halo.  The plan lists, per peer, which owned rows to send and
 where received rows land in the local [owned | halo] ordering of U.
 """
 import numpy as np
 import scipy.sparse as sp
+
+
+def interior_range(indptr, indices, n_own):
+    """Largest contiguous run [a, b) of owned rows that reference NO halo column (column index >= n_own).  With a
+    locality-preserving vertex order the boundary rows sit at the two ends of a rank's range, so one run covers almost
+    everything; the rows outside it are processed after the halo exchange has completed."""
+    row_has_halo = np.zeros(n_own, dtype=bool)
+    if indices.size:
+        rows = np.repeat(np.arange(n_own), np.diff(indptr[:n_own + 1]))
+        row_has_halo[rows[indices[:indptr[n_own]] >= n_own]] = True
+    if not row_has_halo.any():
+        return 0, n_own
+    # longest run of False
+    padded = np.concatenate([[True], row_has_halo, [True]])
+    edges = np.flatnonzero(padded)
+    gaps = np.diff(edges) - 1
+    i = int(np.argmax(gaps))
+    a = int(edges[i])            # index in `padded` of the True before the run -> run starts at padded index a + 1 = row a
+    return a, a + int(gaps[i])
+
+
+def z_order(verts):
+    """Vertex permutation for band partitioning: ascending z (stable).  Contiguous ranges of the permuted mesh are
+    latitude bands, so every rank touches at most two neighbours and the halo is two rings of vertices."""
+    return np.argsort(np.asarray(verts)[:, 2], kind="stable")
+
+
+def permute_mesh(verts, tris, perm):
+    """Relabel vertices: new vertex i = old vertex perm[i]."""
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(perm.size)
+    return np.asarray(verts)[perm], inv[np.asarray(tris)]
 
 
 def split_ranges(n, world):
@@ -52,6 +85,7 @@ class LevelPlan:
             B.sort_indices()
             return B
         self.K_local, self.M_local = localise(Kl), localise(Ml)
+        self.interior = interior_range(self.K_local.indptr, self.K_local.indices, self.n_own)
         self.send = {}                                               # filled by exchange_requests()
 
     def requests(self):

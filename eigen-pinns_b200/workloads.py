@@ -75,6 +75,8 @@ class _GridPlan:
                 assert sel[-1] - sel[0] + 1 == sel.size
                 self.recv[p] = (int(sel[0]), int(sel.size))
         self.send = {}
+        # rows of the first and last owned grid row reference the halo; everything between is interior
+        self.interior = (size, self.n_own - size) if self.n_own > 2 * size else (0, 0)
 
     def requests(self):
         return {p: self.halo_global[o:o + c] for p, (o, c) in self.recv.items()}

@@ -149,6 +149,13 @@ EP_API int ep_eigen_bwd_fused_sym_f32(int n, int k, const int32_t* rowptr, const
                                float out_scale, const float* out_scale_dev, float* dU, int ldo,
                                ep_stream_t stream);
 
+/* Same, for the output rows [row0, row0 + n_rows) only (all pointers keep their row-0 bases).  The vertex-sharded step
+ * computes the interior rows while the halo rows of KU / MU are in flight, then the boundary rows. */
+EP_API int ep_eigen_bwd_fused_sym_rows_f32(int row0, int n_rows, int k, const int32_t* rowptr, const int32_t* col,
+                                    const float* valK, const float* valM, const float* KU, const float* MU, int ld,
+                                    const float* coef, float out_scale, const float* out_scale_dev, float* dU, int ldo,
+                                    ep_stream_t stream);
+
 /* ---- column M-normalisation: multigrid_model.py:120-130, :366-380 ----------------------
  * out[:, j] = U[:, j] / sqrt(colsum_j + 1e-12) where colsum_j = sum_i U_ij MU_ij is read from
  * the diagonal of a partials block (G_jj).  */

@@ -49,6 +49,41 @@ def test_emulated_partition_equals_global(world):
     assert sum(pl.n_own for pl in plans) == n
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_interior_rows_reference_no_halo_and_band_order_balances_halos(world):
+    """interior range: every row inside references owned columns only, the rows just outside reference the halo.
+    Band (z) ordering of an icosphere: every rank talks to at most two peers and the halos are balanced - the
+    generator's face-by-face order puts all icosahedron-edge vertices on rank 0 (7 peers, 6x the halo)."""
+    syn = importlib.import_module("eigen-pinns_b200.synthetic")
+    fem = importlib.import_module("eigen-pinns_b200.fem")
+    v, t = syn.icosphere(24)
+    v2, t2 = partition.permute_mesh(v, t, partition.z_order(v))
+    K, M = fem.assemble_stiffness_mass(v2, t2)
+    K0, M0 = fem.assemble_stiffness_mass(v, t)
+    # the permutation relabels vertices, nothing else: spectra of the two operator pairs agree
+    assert abs(K.diagonal().sum() - K0.diagonal().sum()) < 1e-9 and abs(M.sum() - M0.sum()) < 1e-12
+    plans = partition.build_plans(K, M, world)
+    halos = []
+    for pl in plans:
+        a, b = pl.interior
+        A = pl.K_local.tocsr()
+        assert 0 <= a <= b <= pl.n_own
+        if b > a:
+            assert A[a:b].indices.max() < pl.n_own
+        if a > 0:
+            assert A[a - 1].indices.max() >= pl.n_own
+        if b < pl.n_own:
+            assert A[b].indices.max() >= pl.n_own
+        assert len(pl.recv) <= 2
+        assert (b - a) >= 0.5 * pl.n_own                     # the interior is most of the range
+        halos.append(pl.n_halo)
+    inner = halos[1:-1] if world > 2 else halos
+    assert max(inner) <= 2.0 * min(inner)
+    plans0 = partition.build_plans(K0, M0, world)
+    if world >= 4:
+        assert max(len(pl.recv) for pl in plans0) > 2            # what the reordering fixes
+
+
 def _worker(rank, world, port, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -61,8 +96,16 @@ def _worker(rank, world, port, out_dir):
         rows = torch.zeros(plan.n_own + plan.n_halo, k)
         rows[:plan.n_own] = torch.from_numpy(U[plan.lo:plan.hi])
         ex = de.HaloExchanger(plan, torch.device("cpu"), lambda r, idx, out: torch.index_select(r, 0, idx.long(), out=out))
+        pending = ex.start(rows, plan.n_own)                  # split form used for interior / boundary overlap
+        for w in pending:
+            w.wait()
+        assert np.array_equal(rows[plan.n_own:].numpy(), U[plan.halo_global])
+        rows[plan.n_own:] = 0
         ex.exchange(rows, plan.n_own)
         assert np.array_equal(rows[plan.n_own:].numpy(), U[plan.halo_global])
+        a, b = plan.interior                                  # interior rows do not need the halo at all
+        part_int = plan.K_local.astype(np.float32)[a:b, :plan.n_own] @ rows[:plan.n_own].numpy()
+        np.testing.assert_allclose(part_int, (K.astype(np.float32) @ U)[plan.lo + a:plan.lo + b], rtol=1e-5, atol=1e-5)
         KU_loc = plan.K_local.astype(np.float32) @ rows.numpy()
         ref = (K.astype(np.float32) @ U)[plan.lo:plan.hi]
         np.testing.assert_allclose(KU_loc, ref, rtol=1e-5, atol=1e-5)
