@@ -60,8 +60,17 @@ def main():
     if rank == 0:
         print("MULTI_GPU_CHECK", "OK" if flag.item() == 1.0 else "FAIL", "world", world, "mode", mode,
               "loss_single", l1[:, 5].tolist(), "loss_sharded", l2[:, 5].tolist(), "param_err", perr)
-    dist.destroy_process_group()
-    sys.exit(0 if flag.item() == 1.0 else 1)
+    _leave(flag.item() == 1.0)
+
+
+def _leave(ok):
+    """Tearing the NCCL communicator down while captured CUDA graphs still reference it can block for minutes
+    (torch 2.11 / NCCL 2.28): synchronise, flush and leave without the orderly shutdown."""
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0 if ok else 1)
 
 
 def torus_check(mode, rank, world, dev):
@@ -84,8 +93,7 @@ def torus_check(mode, rank, world, dev):
     if rank == 0:
         print("MULTI_GPU_CHECK", "OK" if flag.item() == 1.0 else "FAIL", "torus world", world, mlp_mode,
               "loss_single", l1[:, 5].tolist(), "loss_sharded", l2[:, 5].tolist(), "param_err", perr)
-    dist.destroy_process_group()
-    sys.exit(0 if flag.item() == 1.0 else 1)
+    _leave(flag.item() == 1.0)
 
 
 if __name__ == "__main__":

@@ -12,8 +12,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _worlds():
+    """World sizes to test: EP_TEST_WORLDS (comma separated) or, by default, 2 and the largest power of two the box has."""
     n = torch.cuda.device_count() if torch.cuda.is_available() else 0
-    return [w for w in (2, 4, 8) if w <= n]
+    env = os.environ.get("EP_TEST_WORLDS")
+    if env:
+        return [int(w) for w in env.split(",") if int(w) <= n]
+    fit = [w for w in (2, 4, 8) if w <= n]
+    return sorted(set(fit[:1] + fit[-1:]))
 
 
 @pytest.mark.parametrize("mode,launch", [("fp32", "eager"), ("bf16", "eager"), ("bf16", "graph"), ("torus_fp32", "eager"),
