@@ -14,7 +14,7 @@ namespace {
 constexpr int kPartialThreads = 256;
 __device__ __forceinline__ bool ep_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-__host__ __device__ inline int partials_len(int k) { return k * k + 4 * k; }
+__host__ __device__ inline int partials_len(int k) { return k * k + 5 * k; }   // G | num | sKK | sKM | sMM | colsum(MU)
 
 inline int partial_blocks(int n, int rows_per_tile) {
   int tiles = ep::ceil_div(n, rows_per_tile);
@@ -49,13 +49,13 @@ eigen_partials_kernel(int n, int k, const float* __restrict__ U, int ldu, const 
 
   double g64[TG][TG];
   float g32[TG][TG];
-  double c64[4][CPL];
+  double c64[5][CPL];
 #pragma unroll
   for (int i = 0; i < TG; ++i)
 #pragma unroll
     for (int j = 0; j < TG; ++j) { g64[i][j] = 0.0; g32[i][j] = 0.f; }
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
+  for (int q = 0; q < 5; ++q)
 #pragma unroll
     for (int c = 0; c < CPL; ++c) c64[q][c] = 0.0;
 
@@ -140,16 +140,17 @@ eigen_partials_kernel(int n, int k, const float* __restrict__ U, int ldu, const 
         // fp64 from the first product on: products of two fp32 values are exact in fp64, so the one-pass
         // expansion sKK - 2 lam sKM + lam^2 sMM keeps ~9 digits even when the residual is 1e-4 of |KU|
         // (near convergence); B200 issues DFMA at half the FFMA rate and this loop is 4 DFMA per 12 bytes.
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
         for (int r = warp; r < R; r += kPartialThreads / 32) {
           const double u = (double)Us[r][c], ku = (double)KUs[r][c], mu = (double)MUs[r][c];
           s0 = fma(u, ku, s0);
           s1 = fma(ku, ku, s1);
           s2 = fma(ku, mu, s2);
           s3 = fma(mu, mu, s3);
+          s4 += mu;                                  // 1^T M U  (zero-mean term of the notebook variants)
         }
         c64[0][cc] += s0; c64[1][cc] += s1;
-        c64[2][cc] += s2; c64[3][cc] += s3;
+        c64[2][cc] += s2; c64[3][cc] += s3; c64[4][cc] += s4;
       }
     }
   }
@@ -186,7 +187,7 @@ eigen_partials_kernel(int n, int k, const float* __restrict__ U, int ldu, const 
         if (a_ < k && b_ < k) out[a_ * k + b_] = g64[i][j];
       }
   }
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < 5; ++q) {
     __syncthreads();
 #pragma unroll
     for (int cc = 0; cc < CPL; ++cc) {
@@ -228,8 +229,8 @@ __device__ double block_sum_256(double v, double* scratch) {
 __global__ void __launch_bounds__(256)
 eigen_finalize_kernel(int k, double n_global, const double* __restrict__ P, float w_res, float w_orth,
                       int flags, const float* __restrict__ lam_target, float w_trace, float w_order,
-                      float w_eigen, const float* __restrict__ lam_bar_extra, float* __restrict__ lam_out,
-                      float* __restrict__ coef, double* __restrict__ loss_acc) {
+                      float w_eigen, float w_mean, float w_smooth, const float* __restrict__ lam_bar_extra,
+                      float* __restrict__ lam_out, float* __restrict__ coef, double* __restrict__ loss_acc) {
   __shared__ double s_lam[128];
   __shared__ double scratch[8];
   const int tid = threadIdx.x;
@@ -239,6 +240,7 @@ eigen_finalize_kernel(int k, double n_global, const double* __restrict__ P, floa
   const double* sKK = num + k;
   const double* sKM = sKK + k;
   const double* sMM = sKM + k;
+  const double* sMU = sMM + k;                    // column sums of M U
   double res_j = 0.0, lam_j = 0.0, den_j = 1.0;
   if (tid < k) {
     den_j = G[(size_t)tid * k + tid] + 1e-12;
@@ -276,6 +278,16 @@ eigen_finalize_kernel(int k, double n_global, const double* __restrict__ P, floa
       extra_bar += (double)w_eigen * 2.0 * d / (double)k;
     }
   }
+  // notebook variants, both zero-weighted in src/:
+  //   zero-mean   mean_{j>=1} (1^T M u_j)^2                       (multigrid_gnn_farthest_point_sampling.ipynb cell 0)
+  //   smoothness  sum_j u_j^T K u_j / (n k) = sum_j num_j/(n k)    (multigrid_gnn_refine_fixed.ipynb cell 4, U_pred part)
+  double mean_j = 0.0, smooth_j = 0.0;
+  if (tid < k) {
+    if (tid >= 1 && k > 1) mean_j = sMU[tid] * sMU[tid] / (double)(k - 1);
+    smooth_j = num[tid] / (n_global * (double)k);
+  }
+  const double mean_sum = block_sum_256(mean_j, scratch);
+  const double smooth_sum = block_sum_256(smooth_j, scratch);
   const double tr_sum = block_sum_256(tr, scratch);
   const double ord_sum = block_sum_256(ordr, scratch);
   const double eig_sum = block_sum_256(eig, scratch);
@@ -288,12 +300,14 @@ eigen_finalize_kernel(int k, double n_global, const double* __restrict__ P, floa
   if (tid < k) {
     double lam_bar = -c_res * (sKM[tid] - lam_j * sMM[tid]) + extra_bar;
     if (lam_bar_extra != nullptr) lam_bar += (double)lam_bar_extra[tid];
-    const double num_bar = lam_bar / den_j;
+    const double num_bar = lam_bar / den_j + (double)w_smooth / (n_global * (double)k);
     den_bar_j = -lam_bar * lam_j / den_j;
     c_lam[tid] = (float)lam_j;
     c_num[tid] = (float)num_bar;
     c_den[tid] = (float)den_bar_j;
     if (lam_out) lam_out[tid] = (float)lam_j;
+    // dL/d(MU)_ij of the zero-mean term is the same for every row i: g_j = 2 w_mean (1^T M u_j) / (k - 1)
+    coef[1 + 3 * k + k * k + tid] = (tid >= 1 && k > 1) ? (float)(2.0 * (double)w_mean * sMU[tid] / (double)(k - 1)) : 0.f;
   }
   __syncthreads();
   const double go = 2.0 * (double)w_orth / (double)k;
@@ -305,12 +319,14 @@ eigen_finalize_kernel(int k, double n_global, const double* __restrict__ P, floa
     coef[0] = (float)c_res;
     const double t0 = (double)w_res * L_res, t1 = (double)w_orth * L_orth;
     const double t2 = (double)w_trace * tr_sum, t3 = (double)w_order * ord_sum, t4 = (double)w_eigen * eig_sum;
+    const double t7 = (double)w_mean * mean_sum, t8 = (double)w_smooth * smooth_sum;
+    const double tot = t0 + t1 + t2 + t3 + t4 + t7 + t8;
     if (flags & EP_FINALIZE_OVERWRITE) {      // first level of a step: no separate zero-fill launch
       loss_acc[0] = t0; loss_acc[1] = t1; loss_acc[2] = t2; loss_acc[3] = t3; loss_acc[4] = t4;
-      loss_acc[5] = t0 + t1 + t2 + t3 + t4;
+      loss_acc[5] = tot; loss_acc[6] = 0.0; loss_acc[7] = t7; loss_acc[8] = t8;
     } else {
       loss_acc[0] += t0; loss_acc[1] += t1; loss_acc[2] += t2; loss_acc[3] += t3; loss_acc[4] += t4;
-      loss_acc[5] += t0 + t1 + t2 + t3 + t4;
+      loss_acc[5] += tot; loss_acc[7] += t7; loss_acc[8] += t8;
     }
   }
 }
@@ -339,6 +355,7 @@ eigen_bwd_prepare_kernel(int n, int k, const float* __restrict__ U, int ldu, con
   const float* c_num = c_lam + k;
   const float* c_den = c_num + k;
   const float* c_G = c_den + k;
+  const float* c_mean = c_G + k * k;
   for (int e = tid; e < KP * KP; e += 256) {
     const int a = e / KP, b = e - a * KP;
     float g = 0.f;
@@ -400,7 +417,7 @@ eigen_bwd_prepare_kernel(int n, int k, const float* __restrict__ U, int ldu, con
         const float lam = s_lam[c], a = s_a[c];
         const float rbar = c_res * (ku - lam * mu);
         KU_bar[(size_t)row * ld + c] = rbar + a * u;
-        MU_bar[(size_t)row * ld + c] = acc1[i][j] - lam * rbar;
+        MU_bar[(size_t)row * ld + c] = acc1[i][j] - lam * rbar + c_mean[c];
         D[(size_t)row * ld + c] = fmaf(a, ku, acc2[i][j]);
       }
     }
@@ -437,6 +454,7 @@ eigen_bwd_fused_sym_kernel(int row0, int n, int k, int lpr_shift, const int32_t*
     if (m == j) v += 2.f * c_den[m];
     S[e] = v;
   }
+  const float* c_mean = c_G + k * k;
   for (int e = threadIdx.x; e < k; e += blockDim.x) { s_lam[e] = c_lam[e]; s_a2[e] = 2.f * c_num[e]; }
   __syncthreads();
 
@@ -447,6 +465,7 @@ eigen_bwd_fused_sym_kernel(int row0, int n, int k, int lpr_shift, const int32_t*
   const int cofs = active ? 4 * lane_r : 0;
   const float4 lam4 = *reinterpret_cast<const float4*>(s_lam + cofs);
   const float4 a24 = *reinterpret_cast<const float4*>(s_a2 + cofs);
+  const float4 gm4 = make_float4(__ldg(c_mean + cofs), __ldg(c_mean + cofs + 1), __ldg(c_mean + cofs + 2), __ldg(c_mean + cofs + 3));
   const long long groups_per_grid = ((long long)gridDim.x * blockDim.x) >> lpr_shift;
   for (long long ri = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> lpr_shift;
        ri < (long long)((n + groups_per_grid - 1) / groups_per_grid) * groups_per_grid; ri += groups_per_grid) {
@@ -455,6 +474,7 @@ eigen_bwd_fused_sym_kernel(int row0, int n, int k, int lpr_shift, const int32_t*
     const int start = valid ? __ldg(rowptr + row) : 0;
     const int end = valid ? __ldg(rowptr + row + 1) : 0;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float m_rowsum = 0.f;                           // (M 1)_i : the zero-mean term's dL/dU_i = (M 1)_i g
     if (active) {
       for (int j = start; j < end; j += 4) {
         int c[4]; float kk[4], mm[4];
@@ -464,6 +484,7 @@ eigen_bwd_fused_sym_kernel(int row0, int n, int k, int lpr_shift, const int32_t*
           c[u] = ok ? __ldg(col + j + u) : -1;
           kk[u] = ok ? __ldg(valK + j + u) : 0.f;
           mm[u] = ok ? __ldg(valM + j + u) : 0.f;
+          m_rowsum += mm[u];
         }
         float4 ku[4], mu[4];
 #pragma unroll
@@ -482,7 +503,8 @@ eigen_bwd_fused_sym_kernel(int row0, int n, int k, int lpr_shift, const int32_t*
         }
       }
     }
-    acc.x *= c_res; acc.y *= c_res; acc.z *= c_res; acc.w *= c_res;
+    acc.x = fmaf(acc.x, c_res, m_rowsum * gm4.x); acc.y = fmaf(acc.y, c_res, m_rowsum * gm4.y);
+    acc.z = fmaf(acc.z, c_res, m_rowsum * gm4.z); acc.w = fmaf(acc.w, c_res, m_rowsum * gm4.w);
     float4 mu_i = make_float4(0.f, 0.f, 0.f, 0.f);
     if (active && valid) {
       const float4 ku_i = __ldg(reinterpret_cast<const float4*>(KU + (size_t)row * ld + cofs));
@@ -547,6 +569,8 @@ eigen_bwd_fused_sym_k32_kernel(int row0, int n, const int32_t* __restrict__ rowp
   const float4 lam4 = make_float4(__ldg(c_lam + cofs), __ldg(c_lam + cofs + 1), __ldg(c_lam + cofs + 2), __ldg(c_lam + cofs + 3));
   const float4 a24 = make_float4(2.f * __ldg(c_num + cofs), 2.f * __ldg(c_num + cofs + 1), 2.f * __ldg(c_num + cofs + 2),
                                  2.f * __ldg(c_num + cofs + 3));
+  const float* c_mean = c_G + k * k;
+  const float4 gm4 = make_float4(__ldg(c_mean + cofs), __ldg(c_mean + cofs + 1), __ldg(c_mean + cofs + 2), __ldg(c_mean + cofs + 3));
   const long long rows_per_grid = (long long)gridDim.x * 32;                  // 8 warps x 4 rows per CTA
   const long long n_iter = ((long long)n + rows_per_grid - 1) / rows_per_grid;
   for (long long it = 0; it < n_iter; ++it) {
@@ -556,6 +580,7 @@ eigen_bwd_fused_sym_k32_kernel(int row0, int n, const int32_t* __restrict__ rowp
     const int start = valid ? __ldg(rowptr + row) : 0;
     const int end = valid ? __ldg(rowptr + row + 1) : 0;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float m_rowsum = 0.f;
     for (int j = start; j < end; j += 4) {
       int c[4]; float kk[4], mm[4];
 #pragma unroll
@@ -564,6 +589,7 @@ eigen_bwd_fused_sym_k32_kernel(int row0, int n, const int32_t* __restrict__ rowp
         c[u] = ok ? __ldg(col + j + u) : -1;
         kk[u] = ok ? __ldg(valK + j + u) : 0.f;
         mm[u] = ok ? __ldg(valM + j + u) : 0.f;
+        m_rowsum += mm[u];
       }
       float4 ku[4], mu[4];
 #pragma unroll
@@ -581,7 +607,8 @@ eigen_bwd_fused_sym_k32_kernel(int row0, int n, const int32_t* __restrict__ rowp
         acc.w = fmaf(kk[u] - lam4.w * mm[u], ku[u].w - lam4.w * mu[u].w, acc.w);
       }
     }
-    acc.x *= c_res; acc.y *= c_res; acc.z *= c_res; acc.w *= c_res;
+    acc.x = fmaf(acc.x, c_res, m_rowsum * gm4.x); acc.y = fmaf(acc.y, c_res, m_rowsum * gm4.y);
+    acc.z = fmaf(acc.z, c_res, m_rowsum * gm4.z); acc.w = fmaf(acc.w, c_res, m_rowsum * gm4.w);
     float4 mu_i = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) {
       const float4 ku_i = __ldg(reinterpret_cast<const float4*>(KU + (size_t)row * ld + cofs));
@@ -651,6 +678,17 @@ axpy_out_kernel(size_t n, float alpha, const float* __restrict__ alpha_dev, cons
     out[i] = __fadd_rn(a[i], __fmul_rn(al, b[i]));     // corr = scale*raw (rounded), U = base + corr
 }
 
+// loss_acc[slot] += w * sum_j v[j] and loss_acc[5] (total) likewise: device-side bookkeeping of terms that are
+// assembled from existing kernels (projection term), so a captured CUDA graph needs no host arithmetic
+__global__ void loss_add_sum_kernel(int len, const double* __restrict__ v, double w, int slot, double* __restrict__ loss_acc) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int j = 0; j < len; ++j) s += v[j];
+    loss_acc[slot] += w * s;
+    loss_acc[5] += w * s;
+  }
+}
+
 int stream_grid(size_t total) {
   size_t g = (total + 255) / 256;
   const size_t cap = (size_t)ep::sm_count() * 16;
@@ -670,7 +708,7 @@ size_t ep_eigen_partials_workspace_bytes(int k) {
   return sizeof(double) * (size_t)partials_len(k) * (size_t)(ep::sm_count() * 4);
 }
 
-size_t ep_eigen_coef_len(int k) { return k > 0 ? (size_t)(1 + 3 * k + k * k) : 0; }
+size_t ep_eigen_coef_len(int k) { return k > 0 ? (size_t)(1 + 4 * k + k * k) : 0; }
 
 int ep_eigen_partials_f32(int n, int k, const float* U, int ldu, const float* KU, const float* MU, int ld,
                           double* out, void* workspace, size_t workspace_bytes, ep_stream_t stream) {
@@ -699,15 +737,22 @@ int ep_eigen_partials_f32(int n, int k, const float* U, int ldu, const float* KU
 
 int ep_eigen_finalize_f32(int k, double n_global, const double* partials, float w_res, float w_orth,
                           int flags, const float* lam_target, float w_trace, float w_order, float w_eigen,
-                          const float* lam_bar_extra, float* lam_out, float* coef, double* loss_acc,
-                          ep_stream_t stream) {
+                          float w_mean, float w_smooth, const float* lam_bar_extra, float* lam_out, float* coef,
+                          double* loss_acc, ep_stream_t stream) {
   EP_REQUIRE(k > 0 && k <= 128, "k out of range");
   EP_REQUIRE(n_global > 0, "n_global must be positive");
   EP_REQUIRE(partials && coef && loss_acc, "null pointer");
   eigen_finalize_kernel<<<1, 256, 0, ep::as_stream(stream)>>>(k, n_global, partials, w_res, w_orth, flags,
-                                                               lam_target, w_trace, w_order, w_eigen,
-                                                               lam_bar_extra, lam_out, coef, loss_acc);
+                                                               lam_target, w_trace, w_order, w_eigen, w_mean,
+                                                               w_smooth, lam_bar_extra, lam_out, coef, loss_acc);
   EP_LAUNCH_CHECK("eigen_finalize_kernel");
+  return EP_OK;
+}
+
+int ep_loss_add_sum_f64(int len, const double* values, double weight, int slot, double* loss_acc, ep_stream_t stream) {
+  EP_REQUIRE(len > 0 && values && loss_acc && slot >= 0 && slot < 9 && slot != 5, "bad argument");
+  loss_add_sum_kernel<<<1, 32, 0, ep::as_stream(stream)>>>(len, values, weight, slot, loss_acc);
+  EP_LAUNCH_CHECK("loss_add_sum_kernel");
   return EP_OK;
 }
 

@@ -86,6 +86,7 @@ class ShardedTrainStepEngine(TrainStepEngine):
         super().__init__(h_local, U_base_local, pairs, offsets, params, cfg, lam_target, mlp_mode)
         self.halo = [HaloExchanger(pl, dev, lambda rows, idx, out: ops.gather_rows(rows, idx, out=out), group) for pl in plans]
         self.overlap = True                     # interior rows while the halo is in flight
+        self._grad_work = []
         self.dCorr.zero_()                      # halo rows never receive a gradient on this rank
 
     def _mlp_rows(self):
@@ -104,8 +105,18 @@ class ShardedTrainStepEngine(TrainStepEngine):
     def _reduce_partials(self, li):
         dist.all_reduce(self.partials[li], group=self.group)
 
+    def _layer_grads_ready(self, l):
+        """All-reduce the [W_l | b_l] block of the flat gradient as soon as the backward has produced it: the transfers
+        of the last layers overlap the kernels of the earlier ones; only layer 0's (the smallest) is exposed."""
+        a, b = self.params.layer_range[l]
+        self._grad_work.append(dist.all_reduce(self.params.grad[a:b], group=self.group, async_op=True))
+
     def _reduce_grads(self):
-        dist.all_reduce(self.params.grad, group=self.group)
+        if not self._grad_work:                                   # backward ran without the hook (unit tests)
+            dist.all_reduce(self.params.grad, group=self.group)
+        for w in self._grad_work:
+            w.wait()
+        self._grad_work = []
 
     def loss_forward(self):
         """Per level: start the halo exchange of U_pred, apply K and M to the interior rows meanwhile, wait, apply them
@@ -126,7 +137,7 @@ class ShardedTrainStepEngine(TrainStepEngine):
             ops.eigen_finalize(self.k, self._n_global(li), self.partials[li], c.w_res, c.w_orth, self.loss_acc,
                                coef=self.coefs[li], lam_out=self.lams[li], level0=(li == 0),
                                lam_target=self.lam_target, w_trace=c.w_trace, w_order=c.w_order, w_eigen=c.w_eigen,
-                               overwrite=(li == 0))
+                               overwrite=(li == 0), w_mean=c.w_mean, w_smooth=c.w_smooth)
 
     def loss_backward(self, scale, scale_dev=None):
         """K U and M U live side by side in one row (engine.KUMU), so their halo rows travel as ONE message; the

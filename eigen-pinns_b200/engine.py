@@ -31,8 +31,10 @@ class FlatParams:
         self.m = torch.zeros_like(self.flat)
         self.v = torch.zeros_like(self.flat)
         self.W, self.b, self.dW, self.db = [], [], [], []
+        self.layer_range = []                       # (first, last) element of layer l's [W | b] block in the flat buffers
         off = 0
         for w, b in zip(weights, biases):
+            self.layer_range.append((off, off + w.numel() + b.numel()))
             for src, store, gstore in ((w, self.W, self.dW), (b, self.b, self.db)):
                 n = src.numel()
                 view = self.flat[off:off + n].view(src.shape)
@@ -78,7 +80,9 @@ class Fp32Mlp:
             ops.axpy_out(U_base, x, scale, out=U_pred, alpha_dev=scale_dev)
         return x                                    # corr_raw (n x k)
 
-    def backward(self, h, d_out):
+    def backward(self, h, d_out, on_layer_grads=None):
+        """on_layer_grads(l): called as soon as dW / db of layer l are enqueued (the sharded engine starts that
+        layer's gradient all-reduce there, overlapping it with the remaining layers)."""
         L = len(self.p.W)
         dy = d_out
         for l in range(L - 1, -1, -1):
@@ -86,12 +90,17 @@ class Fp32Mlp:
             need_dx = l > 0
             dx = self.dx[l & 1][:, :x.shape[1]] if need_dx else None
             ops.linear_bwd(x, self.p.W[l], dy, need_dx, relu_mask=need_dx, dW=self.p.dW[l], db=self.p.db[l], dX=dx)
+            if on_layer_grads is not None:
+                on_layer_grads(l)
             dy = dx
 
 
 class StepConfig:
     def __init__(self, lr=1e-3, weight_decay=1e-5, corr_scale=10.0, w_res=1000.0, w_orth=10.0, w_trace=0.0,
-                 w_order=0.0, w_eigen=0.0, grad_clip=10.0, beta1=0.9, beta2=0.999, eps=1e-8, ramp_epochs=5000.0):
+                 w_order=0.0, w_eigen=0.0, grad_clip=10.0, beta1=0.9, beta2=0.999, eps=1e-8, ramp_epochs=5000.0,
+                 w_mean=0.0, w_smooth=0.0):
+        # w_mean / w_smooth: per-level zero-mean and smoothness terms of the notebook variants
+        self.w_mean, self.w_smooth = w_mean, w_smooth
         self.lr, self.weight_decay, self.corr_scale = lr, weight_decay, corr_scale
         self.w_res, self.w_orth, self.w_trace, self.w_order, self.w_eigen = w_res, w_orth, w_trace, w_order, w_eigen
         self.grad_clip, self.beta1, self.beta2, self.eps = grad_clip, beta1, beta2, eps
@@ -121,7 +130,8 @@ class TrainStepEngine:
         self.partials = [torch.empty(ws.plen, dtype=torch.float64, device=self.dev) for _ in pairs]
         self.coefs = [torch.empty(ws.clen, **f32) for _ in pairs]
         self.lams = [torch.empty(k, **f32) for _ in pairs]
-        self.loss_acc = torch.zeros(6, dtype=torch.float64, device=self.dev)
+        self.loss_acc = torch.zeros(ops.N_LOSS_TERMS, dtype=torch.float64, device=self.dev)
+        self.projections = {}          # level index -> ops.ProjectionTerm (optional notebook-variant term)
         self.lam_target = lam_target.to(**f32).contiguous() if lam_target is not None else None
         self.mlp_mode = mlp_mode
         self.n_mlp = self._mlp_rows()                  # rows the corrector is evaluated on (all, unless sharded)
@@ -138,6 +148,15 @@ class TrainStepEngine:
         self.fused_bwd = True          # symmetric operators: one-pass analytic backward
 
     # ---- pieces (also used one by one by the tests)
+    def add_projection_term(self, level, P, U_coarse, w_proj):
+        """Enable w_proj * sum (P^T U_level - U_coarse)^2 / (n_c k) on `level` (P: scipy n_level x n_c prolongation)."""
+        from .sparse import CsrMatrix
+        import scipy.sparse as sp
+        P = sp.csr_matrix(P)
+        self.projections[level] = ops.ProjectionTerm(CsrMatrix.from_scipy(P, self.dev), CsrMatrix.from_scipy(P.T.tocsr(), self.dev),
+                                                     U_coarse.to(device=self.dev, dtype=torch.float32), w_proj)
+        self._graph = None
+
     def scale_for(self, epoch):
         return self.cfg.corr_scale * min(1.0, epoch / self.cfg.ramp_epochs)
 
@@ -148,7 +167,7 @@ class TrainStepEngine:
 
     def mlp_backward(self):
         m = self.n_mlp
-        self.mlp.backward(self.h[:m], self.dCorr[:m])
+        self.mlp.backward(self.h[:m], self.dCorr[:m], on_layer_grads=self._layer_grads_ready)
 
     def _level_slices(self, li):
         off, n = self.offsets[li], self.pairs[li].n
@@ -164,19 +183,25 @@ class TrainStepEngine:
             ops.eigen_finalize(self.k, self._n_global(li), self.partials[li], c.w_res, c.w_orth, self.loss_acc,
                                coef=self.coefs[li], lam_out=self.lams[li], level0=(li == 0),
                                lam_target=self.lam_target, w_trace=c.w_trace, w_order=c.w_order, w_eigen=c.w_eigen,
-                               overwrite=(li == 0))
+                               overwrite=(li == 0), w_mean=c.w_mean, w_smooth=c.w_smooth)
+        for li, term in self.projections.items():
+            term.forward(self.U_pred[self._level_slices(li)], self.loss_acc)
 
     def loss_backward(self, scale, scale_dev=None):
         for li, pair in enumerate(self.pairs):
             s = self._level_slices(li)
             if self.fused_bwd and ops.eigen_bwd_fused_ok(pair, self.k, self.KU[s], self.MU[s], self.dCorr[s]):
                 ops.eigen_bwd_fused(pair, self.KU[s], self.MU[s], self.coefs[li], scale, self.dCorr[s], scale_dev)
+                if li in self.projections:
+                    self.projections[li].backward(self.dCorr[s], scale, scale_dev)
                 continue
             if self._bwd_scratch is None:
                 self._bwd_scratch = [torch.empty_like(self.KU) for _ in range(3)]
             KU_bar, MU_bar, D = self._bwd_scratch
             ops.eigen_bwd_prepare(self.U_pred[s], self.KU[s], self.MU[s], self.coefs[li], KU_bar[s], MU_bar[s], D[s])
             ops.spmm2_sum(pair.KT, pair.MT, KU_bar[s], MU_bar[s], D[s], scale, out=self.dCorr[s], scale_dev=scale_dev)
+            if li in self.projections:
+                self.projections[li].backward(self.dCorr[s], scale, scale_dev)
 
     def optimizer_step(self, lr, hyper_dev=None):
         p, c = self.params, self.cfg
@@ -199,6 +224,8 @@ class TrainStepEngine:
 
     def _reduce_grads(self):
         pass
+
+    _layer_grads_ready = None          # sharded engine: per-layer gradient all-reduce, started inside the backward
 
     def step(self, epoch, lr=None, marks=None):
         """One epoch body.  Returns the device tensor loss_acc = [res, orth, trace, order, eigen, total]
@@ -298,7 +325,7 @@ class LossReader:
     of the GPU, so the reference's `total_loss.item()` every epoch (src/multigrid_model.py:261) costs no bubble."""
 
     def __init__(self, depth=4):
-        self.buf = [torch.empty(6, dtype=torch.float64).pin_memory() for _ in range(depth)]
+        self.buf = [torch.empty(ops.N_LOSS_TERMS, dtype=torch.float64).pin_memory() for _ in range(depth)]
         self.evt = [torch.cuda.Event() for _ in range(depth)]
         self.n = 0
 
@@ -336,11 +363,11 @@ class HostFedPipeline:
         self.u_dev = [torch.empty_like(engine.U_base) for _ in range(2)]
         self.uploaded = [torch.cuda.Event() for _ in range(2)]
         self.consumed = [torch.cuda.Event() for _ in range(2)]
-        self.loss_host = [torch.empty(6, dtype=torch.float64).pin_memory() for _ in range(2)]
+        self.loss_host = [torch.empty(ops.N_LOSS_TERMS, dtype=torch.float64).pin_memory() for _ in range(2)]
         self.done = [torch.cuda.Event() for _ in range(2)]
         self.count = 0
         self.h2d_bytes = self.x_dev[0].numel() * 4 + self.u_dev[0].numel() * 4
-        self.d2h_bytes = 48
+        self.d2h_bytes = 8 * ops.N_LOSS_TERMS
 
     def submit(self, x_host, U_host, epoch, lr=None):
         s = self.count & 1

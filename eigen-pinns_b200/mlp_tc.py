@@ -131,8 +131,9 @@ class TcMlp:
              U_pred.stride(0) if U_pred is not None else 0, _stream())
         return self.corr
 
-    def backward(self, h, d_out):
-        """dW / db of every layer into the flat gradient buffer.  For each layer the dW kernel (side stream) and
+    def backward(self, h, d_out, on_layer_grads=None):
+        """dW / db of every layer into the flat gradient buffer; on_layer_grads(l) is called once dW / db of layer l are
+        enqueued on the current stream (hook for the sharded engine's per-layer gradient all-reduce).  For each layer the dW kernel (side stream) and
         the dX kernel (main stream) run concurrently on half of the SMs each, walking the tiles in the same order:
         the dZ tile that one of them pulls from HBM is an L2 hit for the other, so dZ is read from DRAM once."""
         L = self.L
@@ -148,6 +149,8 @@ class TcMlp:
                 act = self.acts[l - 1] if l > 0 else self.x0
                 call("ep_tc_linear_dw_bf16", self.n, self.dims[l + 1], self.dims[l], dz_w, self.pd[l], _p(dz), _p(act),
                      _p(self.p.dW[l]), _p(self.p.db[l]), _p(self.ws), self.ws_bytes, 0, _stream())
+                if on_layer_grads is not None:
+                    on_layer_grads(l)
             return
         dz, dz_w = self.dz_out, self.pd[-1]
         half = max(1, self.sm_count // 2)
@@ -169,3 +172,5 @@ class TcMlp:
                 if concurrent:
                     main.wait_stream(side)
                 dz, dz_w = nxt, self.pd[l]
+            if on_layer_grads is not None:
+                on_layer_grads(l)

@@ -153,16 +153,20 @@ def eigen_partials(U, KU, MU, out=None):
     return P
 
 
+N_LOSS_TERMS = 9      # [res, orth, trace, order, eigen, TOTAL, projection, zero-mean, smoothness]
+
+
 def eigen_finalize(k, n_global, P, w_res, w_orth, loss_acc, coef=None, lam_out=None, level0=False,
-                   lam_target=None, w_trace=0.0, w_order=0.0, w_eigen=0.0, lam_bar_extra=None, overwrite=False):
+                   lam_target=None, w_trace=0.0, w_order=0.0, w_eigen=0.0, lam_bar_extra=None, overwrite=False,
+                   w_mean=0.0, w_smooth=0.0):
     """level0: add the eigenvalue terms (:326-348); overwrite: loss_acc is set, not accumulated (first level)."""
     ws = EigenWorkspace.get(k, P.device)
     coef = coef if coef is not None else torch.empty(ws.clen, dtype=torch.float32, device=P.device)
     lam_out = lam_out if lam_out is not None else torch.empty(k, dtype=torch.float32, device=P.device)
     flags = (1 if level0 else 0) | (2 if overwrite else 0)
     call("ep_eigen_finalize_f32", k, float(n_global), _ptr(P), float(w_res), float(w_orth), flags,
-         _ptr(lam_target), float(w_trace), float(w_order), float(w_eigen), _ptr(lam_bar_extra), _ptr(lam_out),
-         _ptr(coef), _ptr(loss_acc), _stream())
+         _ptr(lam_target), float(w_trace), float(w_order), float(w_eigen), float(w_mean), float(w_smooth),
+         _ptr(lam_bar_extra), _ptr(lam_out), _ptr(coef), _ptr(loss_acc), _stream())
     return lam_out, coef
 
 
@@ -198,6 +202,40 @@ def eigen_bwd_fused(pair, KU, MU, coef, scale, out, scale_dev=None, rows=None):
          _ptr(pair.M.val), _ptr(KU), _ptr(MU), KU.stride(0), _ptr(coef), float(scale), _ptr(scale_dev), _ptr(out),
          out.stride(0), _stream())
     return out
+
+
+class ProjectionTerm:
+    """w_proj * sum (P^T U - U_coarse)^2 / (n_coarse k) for one fine level (notebook variant, SURVEY 8a-bis:
+    multigrid_gnn_refine_fixed.ipynb cell 0 `train_gnn`).  Forward and analytic backward are assembled from the
+    existing kernels: SpMM with R = P^T, axpy, the partials kernel (its `num` block = column-wise sum of squares),
+    and for the gradient  dL/dU += P (2 w / (n_c k)) (R U - U_c)  one more SpMM."""
+
+    def __init__(self, P_csr: CsrMatrix, R_csr: CsrMatrix, U_coarse, w_proj):
+        self.P, self.R, self.U_c, self.w = P_csr, R_csr, _check(U_coarse.contiguous()), float(w_proj)
+        n_c, k = U_coarse.shape
+        self.denom = float(max(1, n_c * k))
+        dev = U_coarse.device
+        self.proj = torch.empty((n_c, k), dtype=torch.float32, device=dev)
+        self.diff = torch.empty_like(self.proj)
+        self.part = torch.empty(EigenWorkspace.get(k, dev).plen, dtype=torch.float64, device=dev)
+        self.back = torch.empty((P_csr.shape[0], k), dtype=torch.float32, device=dev)
+
+    def forward(self, U, loss_acc):
+        k = U.shape[1]
+        spmm(self.R, U, out=self.proj)
+        axpy_out(self.proj, self.U_c, -1.0, out=self.diff)
+        eigen_partials(self.diff, self.diff, self.diff, out=self.part)            # part[k*k : k*k + k] = sum_i diff^2
+        call("ep_loss_add_sum_f64", k, _off(self.part, k * k), self.w / self.denom, 6, _ptr(loss_acc), _stream())
+
+    def backward(self, dU, scale, scale_dev=None):
+        """dU += scale * P (2 w / denom) diff."""
+        spmm(self.P, self.diff, out=self.back)
+        c = 2.0 * self.w / self.denom
+        if scale_dev is not None:
+            dU.add_(self.back * (scale_dev * c))          # plumbing-level update (device scalar: graph-capturable)
+        else:
+            call("ep_axpy_out_f32", dU.numel(), float(scale) * c, None, _ptr(dU), _ptr(self.back), _ptr(dU), _stream())
+        return dU
 
 
 def m_normalize_columns(U, M: CsrMatrix, eps=1e-12):
@@ -239,7 +277,7 @@ class _EigenLossFn(torch.autograd.Function):
         U_pred = _check(_rowmajor(U_pred))
         k = U_pred.shape[1]
         dev = U_pred.device
-        loss_acc = torch.zeros(6, dtype=torch.float64, device=dev)
+        loss_acc = torch.zeros(N_LOSS_TERMS, dtype=torch.float64, device=dev)
         saved = []
         lams = []
         for pair, off in zip(pairs, offsets):
@@ -264,7 +302,7 @@ class _EigenLossFn(torch.autograd.Function):
         gr = float(g_res) if g_res is not None else 0.0
         go = float(g_orth) if g_orth is not None else 0.0
         dU = torch.zeros_like(U_pred)
-        scratch_acc = torch.zeros(6, dtype=torch.float64, device=U_pred.device)
+        scratch_acc = torch.zeros(N_LOSS_TERMS, dtype=torch.float64, device=U_pred.device)
         for li, (pair, off) in enumerate(zip(ctx.pairs, ctx.offsets)):
             KU, MU, P = ctx.saved[li]
             U = U_pred[off:off + pair.n]

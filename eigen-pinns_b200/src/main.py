@@ -10,6 +10,7 @@ directory (the reference's location).
 import os
 import sys
 
+import diagnostics
 import mesh_helpers
 import samplers
 from config import PINNConfig
@@ -48,6 +49,8 @@ def main(config_file=None):
     if out_dir:
         os.makedirs(out_dir, exist_ok=True)
     mesh_helpers.save_eigenfunctions(mesh, U_refined, config.n_modes, config.vtu_file)
+    print("Running comprehensive diagnostics...")
+    main.last_report = diagnostics.comprehensive_diagnostics(U_refined, mesh, sampler, config)
     return U_refined
 
 

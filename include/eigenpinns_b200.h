@@ -96,11 +96,12 @@ EP_API int ep_spmm_concat_f32(int n, int d, const int32_t* rowptr, const int32_t
  *   out[k*k + 1k ..)     sKK[j]    = sum_i KU[i,j]^2
  *   out[k*k + 2k ..)     sKM[j]    = sum_i KU[i,j] * MU[i,j]
  *   out[k*k + 3k ..)     sMM[j]    = sum_i MU[i,j]^2
+ *   out[k*k + 4k ..)     sMU[j]    = sum_i MU[i,j]                    (1^T M u_j, zero-mean term of the notebooks)
  * (the last three give sum_i (KU - lam MU)^2 of :317-318 without a second pass; num and these
  * three are accumulated in fp64 from the first product on - products of fp32 values are exact in
  * fp64 - so the expansion keeps ~9 digits when the residual is 1e-4 of |KU|, i.e. near convergence).  Partials of all ranks are summed
  * (allreduce) before phase 2.  Deterministic: fixed grid, fixed reduction order. */
-EP_API size_t ep_eigen_partials_len(int k);                        /* k*k + 4*k doubles */
+EP_API size_t ep_eigen_partials_len(int k);                        /* k*k + 5*k doubles */
 EP_API size_t ep_eigen_partials_workspace_bytes(int k);
 EP_API int ep_eigen_partials_f32(int n, int k, const float* U, int ldu, const float* KU, const float* MU,
                           int ld, double* out, void* workspace, size_t workspace_bytes,
@@ -110,30 +111,42 @@ EP_API int ep_eigen_partials_f32(int n, int k, const float* U, int ldu, const fl
  *   lam_j = num_j / (G_jj + 1e-12);  L_res = sum_j(sKK - 2 lam sKM + lam^2 sMM) / (n_global k);
  *   L_orth = sum_ab (G_ab - I_ab)^2 / k;  and for level 0 the eigenvalue terms of :326-348
  *   (trace = mean lam, order = sum relu(lam_j - lam_{j+1}), eigen = mean (lam - lam_target)^2).
- * loss_acc[0..5] += {w_res L_res, w_orth L_orth, w_trace trace, w_order order, w_eigen eigen, total}
+ * and the two additive terms of the notebook variants (weight 0 in src/):
+ *   mean   = sum_{j>=1} (1^T M u_j)^2 / (k - 1)       multigrid_gnn_farthest_point_sampling.ipynb cell 0 ("L_mean")
+ *   smooth = sum_j u_j^T K u_j / (n_global k)         multigrid_gnn_refine_fixed.ipynb cell 4 ("L_smooth_total")
+ * loss_acc (9 doubles) += {w_res L_res, w_orth L_orth, w_trace trace, w_order order, w_eigen eigen, TOTAL,
+ *                          projection (added by the caller, see ep_loss_add_sum_f64), w_mean mean, w_smooth smooth}
  *   (flags & EP_FINALIZE_OVERWRITE: "=" instead of "+=", for the first level of a step)
  * coef receives what the backward needs (layout below, fp32):
  *   coef[0] = c_res = 2 w_res / (n_global k)
  *   coef[1 .. 1+k)      lam
  *   coef[1+k .. 1+2k)   num_bar   (dL/dnum)
  *   coef[1+2k .. 1+3k)  den_bar   (dL/dden)
- *   coef[1+3k .. )      G_bar[a*k+b] = 2 w_orth / k * (G_ab - I_ab)
+ *   coef[1+3k .. 1+3k+k*k)   G_bar[a*k+b] = 2 w_orth / k * (G_ab - I_ab)
+ *   coef[1+3k+k*k .. )  g_mean[j] = 2 w_mean (1^T M u_j) / (k - 1)  (dL/dMU_ij of the zero-mean term, same for all i)
+ * (the smoothness term needs no extra coefficient: it is linear in num, so w_smooth / (n k) is added to num_bar)
  * lam_target may be NULL (eigen term = 0).  flags & EP_FINALIZE_EIGENVALUE_TERMS enables the :326-348
  * terms (the reference applies them to level 0 only).
  * lam_bar_extra (k floats, may be NULL) is added to dL/dlam: the gradient arriving from any
  * further use of the returned eigenvalues (autograd path of the drop-in modules). */
 enum ep_finalize_flags { EP_FINALIZE_EIGENVALUE_TERMS = 1, EP_FINALIZE_OVERWRITE = 2 };
-EP_API size_t ep_eigen_coef_len(int k);                            /* 1 + 3k + k*k floats */
+EP_API size_t ep_eigen_coef_len(int k);                            /* 1 + 4k + k*k floats */
 EP_API int ep_eigen_finalize_f32(int k, double n_global, const double* partials, float w_res, float w_orth,
                           int flags, const float* lam_target, float w_trace, float w_order,
-                          float w_eigen, const float* lam_bar_extra, float* lam_out, float* coef,
-                          double* loss_acc, ep_stream_t stream);
+                          float w_eigen, float w_mean, float w_smooth, const float* lam_bar_extra,
+                          float* lam_out, float* coef, double* loss_acc, ep_stream_t stream);
+/* loss_acc[slot] += weight * sum(values[0..len)) and the same into loss_acc[5] (total).  Bookkeeping for terms that are
+ * assembled from the SpMM / partials kernels on the caller's side - the projection term
+ *   w_proj * sum (P^T U - U_coarse)^2 / (n_coarse k)          (multigrid_gnn_refine_fixed.ipynb cell 0, "L_proj")
+ * = SpMM with P^T, ep_axpy_out_f32, ep_eigen_partials_f32 (its `num` block is the column-wise sum of squares). */
+EP_API int ep_loss_add_sum_f64(int len, const double* values, double weight, int slot, double* loss_acc,
+                        ep_stream_t stream);
 
 /* Phase 3 (backward, per level): analytic gradient of the loss w.r.t. the three tensors it
  * was built from (what autograd derives from :309-322):
  *   R_bar  = c_res (KU - MU lam)
  *   KU_bar = R_bar + U num_bar
- *   MU_bar = -R_bar lam + U den_bar + U G_bar
+ *   MU_bar = -R_bar lam + U den_bar + U G_bar + 1 g_mean^T
  *   D      = KU num_bar + MU den_bar + MU G_bar^T        (direct dependence on U)
  * followed by ep_spmm2_sum_csr_f32(K^T, M^T, KU_bar, MU_bar, D) -> dL/dU. */
 EP_API int ep_eigen_bwd_prepare_f32(int n, int k, const float* U, int ldu, const float* KU, const float* MU,
@@ -141,7 +154,8 @@ EP_API int ep_eigen_bwd_prepare_f32(int n, int k, const float* U, int ldu, const
                              ep_stream_t stream);
 
 /* Phase 3, fused variant for SYMMETRIC K and M (one gather pass, nothing materialised):
- *   dU = out_scale * [ c_res * sum_j (K_ij - lam M_ij)(KU_j - lam MU_j) + 2 num_bar KU_i + MU_i (Gp + Gp^T) ]
+ *   dU = out_scale * [ c_res * sum_j (K_ij - lam M_ij)(KU_j - lam MU_j) + 2 num_bar KU_i + MU_i (Gp + Gp^T)
+ *                      + (sum_j M_ij) g_mean ]
  * with Gp = G_bar + diag(den_bar).  Algebraically equal to prepare + ep_spmm2_sum_csr_f32 when K = K^T,
  * M = M^T.  Needs k % 4 == 0, k <= 128, 16-byte aligned rows (EP_ERR_UNSUPPORTED otherwise). */
 EP_API int ep_eigen_bwd_fused_sym_f32(int n, int k, const int32_t* rowptr, const int32_t* col, const float* valK,

@@ -46,8 +46,8 @@ def test_ctypes_table_matches_header():
 
 def test_sizes_without_gpu():
     cabi = importlib.import_module("eigen-pinns_b200._cabi")
-    assert cabi.query("ep_eigen_partials_len", 32) == 32 * 32 + 4 * 32
-    assert cabi.query("ep_eigen_coef_len", 64) == 1 + 3 * 64 + 64 * 64
+    assert cabi.query("ep_eigen_partials_len", 32) == 32 * 32 + 5 * 32       # G | num | sKK | sKM | sMM | colsum(MU)
+    assert cabi.query("ep_eigen_coef_len", 64) == 1 + 4 * 64 + 64 * 64         # c_res | lam | num_bar | den_bar | G_bar | g_mean
 
 
 def test_ops_reject_cpu_tensors():

@@ -131,3 +131,24 @@ def test_galerkin_level_operators_are_consistent(mods):
     assert abs(Kl - Kl.T).max() < 1e-12 and abs(Ml - Ml.T).max() < 1e-12
     Kf, Mf = s._galerkin_operators(mesh, fem["verts"])
     assert abs(Kf.tocsr() - csr_from_golden(fem, "K", n)).max() < 1e-12
+
+
+def test_diagnostics_alignment_matches_reference(mods):
+    """align_eigenvectors / Procrustes / Rayleigh quotients against fixtures written by the reference's own
+    src/diagnostics.py (oracle/make_golden_diag.py), with sparse operators instead of the reference's dense ones."""
+    sys.modules.pop("diagnostics", None)
+    import diagnostics
+    g, fem = load_golden("diagnostics.npz"), load_golden("bunny_fem.npz")
+    n = fem["verts"].shape[0]
+    K, M = csr_from_golden(fem, "K", n), csr_from_golden(fem, "M", n)
+    U_al, perm, signs = diagnostics.align_eigenvectors(g["U_pred"], fem["evec10"], M)
+    assert np.array_equal(perm, g["permutation"]) and np.array_equal(signs, g["signs"])
+    np.testing.assert_allclose(U_al, g["U_aligned"], rtol=0, atol=1e-14)
+    U_e, perm_e, signs_e = diagnostics.align_eigenvectors(g["U_pred"], fem["evec10"], None)
+    assert np.array_equal(perm_e, g["permutation_euclid"]) and np.array_equal(signs_e, g["signs_euclid"])
+    U_pa, err = diagnostics.get_subspace_error_and_alignment(g["U_pred"], fem["evec10"], M)
+    assert err == pytest.approx(float(g["subspace_error"]), rel=1e-9)
+    np.testing.assert_allclose(U_pa, g["U_procrustes"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(diagnostics.compute_rayleigh_quotients(g["U_pred"], K, M), g["lam_pred"], rtol=1e-9)
+    np.testing.assert_allclose(diagnostics.compute_rayleigh_quotients(fem["evec10"], K, M), g["lam_exact"], rtol=1e-8,
+                               atol=1e-12)

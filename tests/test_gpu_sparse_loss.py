@@ -80,7 +80,7 @@ def test_eigen_partials_against_fp64(k):
     P = ops.eigen_partials(U.to(dev()), KU.to(dev()), MU.to(dev())).cpu().numpy()
     U64, KU64, MU64 = U.double().numpy(), KU.double().numpy(), MU.double().numpy()
     ref = np.concatenate([(U64.T @ MU64).ravel(), (U64 * KU64).sum(0), (KU64 * KU64).sum(0),
-                          (KU64 * MU64).sum(0), (MU64 * MU64).sum(0)])
+                          (KU64 * MU64).sum(0), (MU64 * MU64).sum(0), MU64.sum(0)])
     np.testing.assert_allclose(P, ref, rtol=0, atol=2e-6 * np.sqrt(n) * 4)
     # run twice: deterministic reduction order
     P2 = ops.eigen_partials(U.to(dev()), KU.to(dev()), MU.to(dev())).cpu().numpy()
@@ -207,3 +207,64 @@ def test_fused_symmetric_backward_equals_general_path(k):
     (l_res + l_orth + sum(extra)).backward()
     gref = 0.7 * Uc.grad
     assert (outs[0][0].cpu() - gref).abs().max().item() <= 5e-5 * gref.abs().max().item()
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_notebook_variant_terms_against_autograd(fused):
+    """Zero-mean, smoothness and projection terms (notebooks multigrid_gnn_farthest_point_sampling cell 0,
+    multigrid_gnn_refine_fixed cells 0 and 4) as flags of the engine's eigen-loss: loss terms and dL/dU against a
+    torch-autograd (fp64) restatement of the notebook formulas on the coarse + bunny pair."""
+    import scipy.sparse as sp
+    ops, sparse, engine = pkg("ops"), pkg("sparse"), pkg("engine")
+    from sklearn.neighbors import NearestNeighbors
+    fem, (K, M), (Kc, Mc) = bunny_levels()
+    n, nc, k = K.shape[0], Kc.shape[0], 16
+    g = torch.Generator().manual_seed(4)
+    U = 0.05 * torch.randn(nc + n, k, generator=g)
+    U[:, 0] += 0.02                                                   # a mean component for the zero-mean term
+    dist_, idx = NearestNeighbors(n_neighbors=6).fit(fem["coarse_verts"]).kneighbors(fem["verts"])
+    w = 1.0 / (dist_ + 1e-12)
+    w /= w.sum(1, keepdims=True)
+    P = sp.coo_matrix((w.ravel(), (np.repeat(np.arange(n), 6), idx.ravel())), shape=(n, nc)).tocsr()
+    U_c = 0.05 * torch.randn(nc, k, generator=g)
+    w_res, w_orth, w_mean, w_smooth, w_proj = 1000.0, 10.0, 7.0, 3.0, 11.0
+    # ---- reference: the notebook formulas in fp64 with autograd
+    Ud = U.double().requires_grad_(True)
+    total = torch.zeros((), dtype=torch.float64)
+    terms = {"mean": 0.0, "smooth": 0.0}
+    for (Kl, Ml, off) in ((Kc, Mc, 0), (K, M, nc)):
+        nl = Kl.shape[0]
+        Kt = torch.from_numpy(Kl.astype(np.float32).toarray().astype(np.float64))
+        Mt = torch.from_numpy(Ml.astype(np.float32).toarray().astype(np.float64))
+        Ul = Ud[off:off + nl]
+        Lu, Mu = Kt @ Ul, Mt @ Ul
+        lam = (Ul * Lu).sum(0) / ((Ul * Mu).sum(0) + 1e-12)
+        l_res = ((Lu - Mu * lam) ** 2).mean()
+        l_orth = ((Ul.t() @ Mu - torch.eye(k, dtype=torch.float64)) ** 2).sum() / k
+        l_mean = ((torch.ones(1, nl, dtype=torch.float64) @ Mu[:, 1:]) ** 2).mean()
+        l_smooth = (Ul * Lu).sum() / (nl * k)
+        total = total + w_res * l_res + w_orth * l_orth + w_mean * l_mean + w_smooth * l_smooth
+        terms["mean"] += w_mean * float(l_mean)
+        terms["smooth"] += w_smooth * float(l_smooth)
+    Pt = torch.from_numpy(P.toarray())
+    l_proj = ((Pt.t() @ Ud[nc:] - U_c.double()) ** 2).sum() / (nc * k)
+    total = total + w_proj * l_proj
+    total.backward()
+    # ---- engine
+    h = torch.zeros(nc + n, 4, device=dev())
+    params = engine.FlatParams([torch.zeros(8, 4), torch.zeros(k, 8)], [torch.zeros(8), torch.zeros(k)], dev())
+    cfg = engine.StepConfig(w_res=w_res, w_orth=w_orth, w_mean=w_mean, w_smooth=w_smooth)
+    eng = engine.TrainStepEngine(h, U.to(dev()), [sparse.OperatorPair(Kc, Mc, dev()), sparse.OperatorPair(K, M, dev())],
+                                 [0, nc], params, cfg)
+    eng.fused_bwd = fused
+    eng.add_projection_term(1, P, U_c, w_proj)
+    eng.U_pred.copy_(U.to(dev()))
+    eng.loss_forward()
+    eng.loss_backward(1.0)
+    acc = eng.loss_acc.cpu().numpy()
+    assert acc[5] == pytest.approx(float(total), rel=2e-5)
+    assert acc[6] == pytest.approx(w_proj * float(l_proj), rel=2e-5)
+    assert acc[7] == pytest.approx(terms["mean"], rel=2e-5) and acc[8] == pytest.approx(terms["smooth"], rel=2e-5)
+    gref = Ud.grad.numpy()
+    err = np.abs(eng.dCorr.cpu().numpy() - gref).max()
+    assert err <= 3e-5 * np.abs(gref).max(), err
