@@ -437,7 +437,9 @@ eigen_bwd_fused_sym_kernel(int row0, int n, int k, int lpr_shift, const int32_t*
                            const int32_t* __restrict__ col, const float* __restrict__ valK,
                            const float* __restrict__ valM, const float* __restrict__ KU,
                            const float* __restrict__ MU, int ld, const float* __restrict__ coef, float out_scale_v,
-                           const float* __restrict__ out_scale_dev, float* __restrict__ dU, int ldo) {
+                           const float* __restrict__ out_scale_dev, float* __restrict__ dU, int ldo, int gram_in_out) {
+  // gram_in_out != 0: dU already holds out_scale * MU_i S (tensor-core kernel ep_eigen_bwd_gram_term_tf32x3); the
+  // k x k product below is skipped and the gathered terms are added to it
   const float out_scale = out_scale_dev ? __ldg(out_scale_dev) : out_scale_v;
   extern __shared__ __align__(16) float fsm[];
   float* S = fsm;                 // k x k
@@ -513,6 +515,7 @@ eigen_bwd_fused_sym_kernel(int row0, int n, int k, int lpr_shift, const int32_t*
       acc.z = fmaf(a24.z, ku_i.z, acc.z); acc.w = fmaf(a24.w, ku_i.w, acc.w);
     }
     // acc += MU_i S : lane L of the row group holds MU_i[4L .. 4L+3]
+    if (!gram_in_out)
 #pragma unroll
     for (int L = 0; L < kv; ++L) {
       const float m0 = __shfl_sync(0xffffffffu, mu_i.x, L, lpr);
@@ -530,8 +533,15 @@ eigen_bwd_fused_sym_kernel(int row0, int n, int k, int lpr_shift, const int32_t*
       acc.x = fmaf(m3, s3.x, acc.x); acc.y = fmaf(m3, s3.y, acc.y); acc.z = fmaf(m3, s3.z, acc.z); acc.w = fmaf(m3, s3.w, acc.w);
     }
     if (active && valid) {
-      acc.x *= out_scale; acc.y *= out_scale; acc.z *= out_scale; acc.w *= out_scale;
-      *reinterpret_cast<float4*>(dU + (size_t)row * ldo + cofs) = acc;
+      float4* dst = reinterpret_cast<float4*>(dU + (size_t)row * ldo + cofs);
+      if (gram_in_out) {
+        const float4 t = *dst;
+        acc.x = fmaf(acc.x, out_scale, t.x); acc.y = fmaf(acc.y, out_scale, t.y);
+        acc.z = fmaf(acc.z, out_scale, t.z); acc.w = fmaf(acc.w, out_scale, t.w);
+      } else {
+        acc.x *= out_scale; acc.y *= out_scale; acc.z *= out_scale; acc.w *= out_scale;
+      }
+      *dst = acc;
     }
   }
 }
@@ -780,6 +790,14 @@ int ep_eigen_bwd_fused_sym_rows_f32(int row0, int n, int k, const int32_t* rowpt
                                     const float* valK, const float* valM, const float* KU, const float* MU, int ld,
                                     const float* coef, float out_scale, const float* out_scale_dev, float* dU, int ldo,
                                     ep_stream_t stream) {
+  return ep_eigen_bwd_gather_sym_rows_f32(row0, n, k, rowptr, col, valK, valM, KU, MU, ld, coef, out_scale, out_scale_dev,
+                                          dU, ldo, 0, stream);
+}
+
+int ep_eigen_bwd_gather_sym_rows_f32(int row0, int n, int k, const int32_t* rowptr, const int32_t* col,
+                                     const float* valK, const float* valM, const float* KU, const float* MU, int ld,
+                                     const float* coef, float out_scale, const float* out_scale_dev, float* dU, int ldo,
+                                     int gram_in_out, ep_stream_t stream) {
   EP_REQUIRE(n >= 0 && k > 0 && row0 >= 0, "bad size");
   if (n == 0) return EP_OK;
   EP_REQUIRE(rowptr && col && valK && valM && KU && MU && coef && dU, "null pointer");
@@ -803,7 +821,7 @@ int ep_eigen_bwd_fused_sym_rows_f32(int row0, int n, int k, const int32_t* rowpt
   const long long cap = (long long)ep::sm_count() * 8;
   if (grid > cap) grid = cap;
   cudaStream_t st = ep::as_stream(stream);
-  if (k == 32 && ep::tune_flag(2)) {
+  if (k == 32 && ep::tune_flag(2) && !gram_in_out) {
     long long g32 = ((long long)n + 31) / 32;
     const long long cap32 = (long long)ep::sm_count() * 8;
     if (g32 > cap32) g32 = cap32;
@@ -813,7 +831,7 @@ int ep_eigen_bwd_fused_sym_rows_f32(int row0, int n, int k, const int32_t* rowpt
     return EP_OK;
   }
 #define EP_FUSED_LAUNCH(KVT) eigen_bwd_fused_sym_kernel<KVT><<<(unsigned)grid, 256, smem, st>>>( \
-      row0, n, k, lpr_shift, rowptr, col, valK, valM, KU, MU, ld, coef, out_scale, out_scale_dev, dU, ldo)
+      row0, n, k, lpr_shift, rowptr, col, valK, valM, KU, MU, ld, coef, out_scale, out_scale_dev, dU, ldo, gram_in_out)
   switch (kv) {
     case 4: EP_FUSED_LAUNCH(4); break;
     case 8: EP_FUSED_LAUNCH(8); break;

@@ -195,8 +195,9 @@ class TrainStepEngine:
                 if li in self.projections:
                     self.projections[li].backward(self.dCorr[s], scale, scale_dev)
                 continue
-            if self._bwd_scratch is None:
-                self._bwd_scratch = [torch.empty_like(self.KU) for _ in range(3)]
+            if self._bwd_scratch is None:             # same row stride as KU / MU (halves of the interleaved rows)
+                two = torch.empty_like(self.KUMU)
+                self._bwd_scratch = [two[:, :self.k], two[:, self.k:], torch.empty_like(self.KUMU)[:, :self.k]]
             KU_bar, MU_bar, D = self._bwd_scratch
             ops.eigen_bwd_prepare(self.U_pred[s], self.KU[s], self.MU[s], self.coefs[li], KU_bar[s], MU_bar[s], D[s])
             ops.spmm2_sum(pair.KT, pair.MT, KU_bar[s], MU_bar[s], D[s], scale, out=self.dCorr[s], scale_dev=scale_dev)

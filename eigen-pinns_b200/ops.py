@@ -5,6 +5,7 @@ torch is only the allocator / stream / autograd plumbing.  CPU tensors are rejec
 no fallback path.
 """
 import ctypes
+import os
 
 import torch
 
@@ -172,13 +173,21 @@ def eigen_finalize(k, n_global, P, w_res, w_orth, loss_acc, coef=None, lam_out=N
 
 def eigen_bwd_prepare(U, KU, MU, coef, KU_bar=None, MU_bar=None, D=None):
     n, k = U.shape
-    KU_bar = KU_bar if KU_bar is not None else torch.empty_like(KU)
-    MU_bar = MU_bar if MU_bar is not None else torch.empty_like(KU)
-    D = D if D is not None else torch.empty_like(KU)
+
+    def like_KU():                                # same row stride as KU (which may be one half of an interleaved row)
+        return torch.empty((n, KU.stride(0)), dtype=torch.float32, device=KU.device)[:, :k]
+    KU_bar = KU_bar if KU_bar is not None else like_KU()
+    MU_bar = MU_bar if MU_bar is not None else like_KU()
+    D = D if D is not None else like_KU()
     assert KU.stride(0) == MU.stride(0) == KU_bar.stride(0) == MU_bar.stride(0) == D.stride(0)
     call("ep_eigen_bwd_prepare_f32", n, k, _ptr(U), U.stride(0), _ptr(KU), _ptr(MU), KU.stride(0), _ptr(coef),
          _ptr(KU_bar), _ptr(MU_bar), _ptr(D), _stream())
     return KU_bar, MU_bar, D
+
+
+# k x k term of the backward on the tensor cores (tcgen05 kind::tf32, 3 passes) instead of SIMT shuffles; EP_TC_GRAM=0
+# selects the one-kernel SIMT form
+TENSOR_CORE_GRAM = os.environ.get("EP_TC_GRAM", "1") == "1"
 
 
 def eigen_bwd_fused_ok(pair, k, *tensors):
@@ -198,6 +207,14 @@ def eigen_bwd_fused(pair, KU, MU, coef, scale, out, scale_dev=None, rows=None):
     # the kernel reads row i of KU / MU for output row i: shift those base pointers together with the output;
     # gathered neighbours are addressed from the unshifted bases through absolute column indices, so the shifted
     # call passes the column-relative bases explicitly (gather base = row 0)
+    if TENSOR_CORE_GRAM and k in (16, 32, 64):
+        # k x k product on the tensor cores (TF32 x 3, fp32 accuracy), then the gather pass adds the sparse terms
+        call("ep_eigen_bwd_gram_term_tf32x3", a, b - a, k, _ptr(MU), MU.stride(0), _ptr(coef), float(scale),
+             _ptr(scale_dev), _ptr(out), out.stride(0), _stream())
+        call("ep_eigen_bwd_gather_sym_rows_f32", a, b - a, k, _ptr(pair.K.rowptr), _ptr(pair.K.col), _ptr(pair.K.val),
+             _ptr(pair.M.val), _ptr(KU), _ptr(MU), KU.stride(0), _ptr(coef), float(scale), _ptr(scale_dev), _ptr(out),
+             out.stride(0), 1, _stream())
+        return out
     call("ep_eigen_bwd_fused_sym_rows_f32", a, b - a, k, _ptr(pair.K.rowptr), _ptr(pair.K.col), _ptr(pair.K.val),
          _ptr(pair.M.val), _ptr(KU), _ptr(MU), KU.stride(0), _ptr(coef), float(scale), _ptr(scale_dev), _ptr(out),
          out.stride(0), _stream())

@@ -170,6 +170,18 @@ EP_API int ep_eigen_bwd_fused_sym_rows_f32(int row0, int n_rows, int k, const in
                                     const float* coef, float out_scale, const float* out_scale_dev, float* dU, int ldo,
                                     ep_stream_t stream);
 
+/* Two-kernel form of the same backward with the dense k x k product on the TENSOR CORES (tcgen05 kind::tf32, 3-pass
+ * hi/lo split = fp32 accuracy, accumulators in TMEM):
+ *   1. ep_eigen_bwd_gram_term_tf32x3     dU[row0 .. row0+n) = out_scale * MU_i (Gp + Gp^T)          (k = 16, 32 or 64)
+ *   2. ep_eigen_bwd_gather_sym_rows_f32  with gram_in_out = 1: dU += out_scale * (gathered terms), product skipped
+ * The one-kernel form spends 53 % (k = 32) to 75 % (k = 64) of its time issuing that product with shuffles. */
+EP_API int ep_eigen_bwd_gram_term_tf32x3(int row0, int n_rows, int k, const float* MU, int ld, const float* coef,
+                                  float out_scale, const float* out_scale_dev, float* dU, int ldo, ep_stream_t stream);
+EP_API int ep_eigen_bwd_gather_sym_rows_f32(int row0, int n_rows, int k, const int32_t* rowptr, const int32_t* col,
+                                     const float* valK, const float* valM, const float* KU, const float* MU, int ld,
+                                     const float* coef, float out_scale, const float* out_scale_dev, float* dU, int ldo,
+                                     int gram_in_out, ep_stream_t stream);
+
 /* ---- column M-normalisation: multigrid_model.py:120-130, :366-380 ----------------------
  * out[:, j] = U[:, j] / sqrt(colsum_j + 1e-12) where colsum_j = sum_i U_ij MU_ij is read from
  * the diagonal of a partials block (G_jj).  */

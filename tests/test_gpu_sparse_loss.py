@@ -268,3 +268,52 @@ def test_notebook_variant_terms_against_autograd(fused):
     gref = Ud.grad.numpy()
     err = np.abs(eng.dCorr.cpu().numpy() - gref).max()
     assert err <= 3e-5 * np.abs(gref).max(), err
+
+
+@pytest.mark.parametrize("k", [16, 32, 64])
+@pytest.mark.parametrize("n", [1, 127, 2503, 40001])
+def test_tensor_core_gram_term_matches_fp64(n, k):
+    """ep_eigen_bwd_gram_term_tf32x3: dU = s * MU (Gp + Gp^T) on tcgen05 (TF32 x 3) against fp64, strided inputs."""
+    import ctypes
+    cabi, ops = pkg("_cabi"), pkg("ops")
+    g = torch.Generator().manual_seed(100 * k + n % 97)
+    KUMU = torch.randn(n, 2 * k, generator=g).to(dev())                # MU is the right half of an interleaved row
+    MU = KUMU[:, k:]
+    clen = cabi.query("ep_eigen_coef_len", k)
+    coef = torch.randn(clen, generator=g).to(dev())
+    out = torch.full((n + 3, k), float("nan"), device=dev())           # rows [2, 2 + n) of a larger array are written
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    cabi.call("ep_eigen_bwd_gram_term_tf32x3", 0, n, k, P(MU), MU.stride(0), P(coef), 0.37, None, P(out[2:]), out.stride(0),
+              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    c = coef.double().cpu()
+    G = c[1 + 3 * k:1 + 3 * k + k * k].view(k, k)
+    S = G + G.t() + 2.0 * torch.diag(c[1 + 2 * k:1 + 3 * k])
+    ref = 0.37 * (MU.double().cpu() @ S)
+    got = out[2:2 + n].double().cpu()
+    assert torch.isnan(out[:2]).all() and torch.isnan(out[2 + n:]).all()
+    assert (got - ref).abs().max().item() <= 4e-6 * ref.abs().max().item() * np.sqrt(k / 16.0)
+
+
+def test_tensor_core_backward_equals_simt_backward():
+    """Two-kernel form (tensor-core k x k term + gather) against the one-kernel SIMT form, incl. a row range."""
+    ops, sparse, engine = pkg("ops"), pkg("sparse"), pkg("engine")
+    fem, (K, M), _ = bunny_levels()
+    pair = sparse.OperatorPair(K, M, dev())
+    n = K.shape[0]
+    for k in (16, 32, 64):
+        U = (0.3 * torch.randn(n, k, generator=torch.Generator().manual_seed(k))).to(dev())
+        KUMU = torch.empty(n, 2 * k, device=dev())
+        KU, MU = KUMU[:, :k], KUMU[:, k:]
+        ops.spmm2(pair, U, out_K=KU, out_M=MU)
+        Pp = ops.eigen_partials(U, KU, MU)
+        acc = torch.zeros(ops.N_LOSS_TERMS, dtype=torch.float64, device=dev())
+        _, coef = ops.eigen_finalize(k, n, Pp, 1000.0, 10.0, acc, w_mean=2.0, w_smooth=1.5)
+        outs = []
+        for tc in (False, True):
+            ops.TENSOR_CORE_GRAM = tc
+            d = torch.zeros(n, k, device=dev())
+            ops.eigen_bwd_fused(pair, KU, MU, coef, 0.7, d, rows=(0, 1000))
+            ops.eigen_bwd_fused(pair, KU, MU, coef, 0.7, d, rows=(1000, n))
+            outs.append(d)
+        ops.TENSOR_CORE_GRAM = True
+        assert (outs[0] - outs[1]).abs().max().item() <= 1e-5 * outs[0].abs().max().item()
