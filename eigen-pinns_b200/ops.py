@@ -188,6 +188,9 @@ def eigen_bwd_prepare(U, KU, MU, coef, KU_bar=None, MU_bar=None, D=None):
 # k x k term of the backward on the tensor cores (tcgen05 kind::tf32, 3 passes) instead of SIMT shuffles; EP_TC_GRAM=0
 # selects the one-kernel SIMT form
 TENSOR_CORE_GRAM = os.environ.get("EP_TC_GRAM", "1") == "1"
+# measured on B200: at k = 32 the SIMT product hides behind the gather (0.45 vs 0.54 ms at 1 M vertices), at k = 64 the
+# tensor-core form wins (15.8 vs 16.4 ms at 16.7 M vertices; 21.6 ms before KU / MU were interleaved)
+TENSOR_CORE_GRAM_MIN_K = int(os.environ.get("EP_TC_GRAM_MIN_K", "64"))
 
 
 def eigen_bwd_fused_ok(pair, k, *tensors):
@@ -207,7 +210,7 @@ def eigen_bwd_fused(pair, KU, MU, coef, scale, out, scale_dev=None, rows=None):
     # the kernel reads row i of KU / MU for output row i: shift those base pointers together with the output;
     # gathered neighbours are addressed from the unshifted bases through absolute column indices, so the shifted
     # call passes the column-relative bases explicitly (gather base = row 0)
-    if TENSOR_CORE_GRAM and k in (16, 32, 64):
+    if TENSOR_CORE_GRAM and k in (16, 32, 64) and k >= TENSOR_CORE_GRAM_MIN_K:
         # k x k product on the tensor cores (TF32 x 3, fp32 accuracy), then the gather pass adds the sparse terms
         call("ep_eigen_bwd_gram_term_tf32x3", a, b - a, k, _ptr(MU), MU.stride(0), _ptr(coef), float(scale),
              _ptr(scale_dev), _ptr(out), out.stride(0), _stream())

@@ -49,6 +49,13 @@ def normalize_columns_torch(U, eps=1e-12):
 
 
 def _knn(X_ref, X_query, k):
+    """(distances, indices) of the k nearest reference points, sorted by distance.  With a GPU: the grid-hash kernel
+    (ep_knn_grid_f64, ties by index); without one (pre-processing on a CPU-only host, CPU test-suite): scikit-learn,
+    as in the reference.  Pre-processing is outside the training hot path, which has no CPU path at all."""
+    if torch.cuda.is_available():
+        knn_mod = _backend.module("knn")
+        idx, dist = knn_mod.knn(np.asarray(X_ref, dtype=np.float64), np.asarray(X_query, dtype=np.float64), k)
+        return dist.cpu().numpy(), idx.cpu().numpy()
     from sklearn.neighbors import NearestNeighbors
     nbrs = NearestNeighbors(n_neighbors=k, algorithm='auto').fit(X_ref)
     return nbrs.kneighbors(X_query)
@@ -136,6 +143,15 @@ def orthonormalize(U, M):
             v -= (Q[:, j] @ (M @ v)) * Q[:, j]
         Q[:, i] = v / (np.sqrt(v @ (M @ v)) + 1e-12)
     return Q
+
+
+def jacobi_smooth_device(M, L, U_rough, alpha=0.05, n_iters=5, device="cuda"):
+    """Same sweeps on the GPU in fp32 (each sweep = one CSR SpMM); for meshes where the host loop matters."""
+    knn_mod = _backend.module("knn")
+    pair = _sparse.OperatorPair(L, M, device)                 # K and M on one shared pattern
+    U = knn_mod.jacobi_smooth(pair.M, pair.K, torch.from_numpy(np.asarray(U_rough, dtype=np.float32)).to(device),
+                              alpha=alpha, n_iters=n_iters)
+    return U.cpu().numpy().astype(np.float64)
 
 
 def jacobi_smooth(M, L, U_rough, alpha=0.05, n_iters=5):

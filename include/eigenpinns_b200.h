@@ -323,6 +323,17 @@ EP_API int ep_fem_segment_sum_f64(int64_t nnz, const int64_t* seg_start, const i
                            const int64_t* uniq_keys, int64_t n_verts, int32_t* col, float* valK, float* valM,
                            double* valK64, double* valM64, ep_stream_t stream);
 
+/* ---- "next" row: k nearest neighbours for the aggregation graph and the prolongation (utils.py:39-75) -----------
+ * Replaces sklearn NearestNeighbors(n_neighbors=k).fit(ref).kneighbors(query).  Reference points are binned on a
+ * uniform grid by the caller: cell id = (cx * dims[1] + cy) * dims[2] + cz with c = clip(floor((p - lo) / cell)),
+ * `order` = reference indices sorted by cell id (stable), cell_start[c] .. cell_start[c+1] = the slice of `order` that
+ * lies in cell c (dims[0]*dims[1]*dims[2] + 1 entries).  Distances are fp64 ((dx*dx + dy*dy) + dz*dz, no FMA); ties are
+ * broken by the smaller reference index.  out_idx: n_query x k int64 sorted by (distance, index); out_dist (may be
+ * NULL): the distances.  lo, dims: HOST arrays. */
+EP_API int ep_knn_grid_f64(int64_t n_query, const double* query, int64_t n_ref, const double* ref, const int64_t* order,
+                    const int64_t* cell_start, const double* lo, double cell, const int64_t* dims, int k,
+                    int64_t* out_idx, double* out_dist, ep_stream_t stream);
+
 /* ---- multi-GPU plumbing: halo rows --------------------------------------------------------
  * dst[r, :] = src[idx[r], :]  (pack the boundary rows of U that a peer needs). */
 EP_API int ep_gather_rows_f32(int n_idx, int k, const int32_t* idx, const float* src, int lds,

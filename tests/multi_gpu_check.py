@@ -25,7 +25,7 @@ def main():
     import config as cfg_mod
     import multigrid_model
     de = importlib.import_module("eigen-pinns_b200.dist_engine")
-    w = bench.build_host_workload("icosphere10k")
+    w = bench.build_host_workload("icosphere10k", band_order=True)
     k = w["k"]
     cfg = cfg_mod.PINNConfig.from_yaml(os.path.join(ROOT, "eigen-pinns_b200", "src", "parameters.yml"))
     cfg.n_modes, cfg.mlp_mode, cfg.seed, cfg.hidden_layers = k, mode, 0, [256, 256]

@@ -1,0 +1,67 @@
+"""GPU pre-processing: grid-hash kNN, prolongation, Jacobi smoothing against scikit-learn / scipy and
+the fixtures written by the reference's own utils.py (tests/golden/prep_cgc.npz)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from conftest import load_golden, csr_from_golden
+from gpu_util import pkg, dev, dropin, bunny_levels
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n_ref,n_query,k", [(50, 50, 5), (2503, 2503, 22), (6000, 300, 21), (20000, 20000, 9),
+                                             (100, 1000, 64), (30, 30, 30)])
+def test_knn_matches_sklearn(n_ref, n_query, k):
+    from sklearn.neighbors import NearestNeighbors
+    knn = pkg("knn")
+    rng = np.random.default_rng(n_ref + k)
+    sph = rng.standard_normal((n_ref, 3))
+    R = sph / np.linalg.norm(sph, axis=1)[:, None] * np.array([1.0, 0.7, 1.3])     # points on a surface
+    Q = R if n_query == n_ref else R[rng.integers(0, n_ref, n_query)] + 0.05 * rng.standard_normal((n_query, 3))
+    idx, dist = knn.knn(R, Q, k)
+    idx, dist = idx.cpu().numpy(), dist.cpu().numpy()
+    d_ref, i_ref = NearestNeighbors(n_neighbors=k).fit(R).kneighbors(Q)
+    np.testing.assert_allclose(dist, d_ref, rtol=1e-12, atol=1e-14)
+    assert np.all(np.diff(dist, axis=1) >= 0)
+    same = np.array([set(a) == set(b) for a, b in zip(idx, i_ref)])
+    assert same.mean() > 0.999                                       # exact ties at the k-th distance may differ
+    # returned indices reproduce the returned distances exactly
+    d_chk = np.linalg.norm(R[idx] - Q[:, None, :], axis=2)
+    np.testing.assert_allclose(d_chk, dist, rtol=1e-12, atol=1e-14)
+
+
+def test_knn_ties_break_by_index_on_a_regular_grid():
+    knn = pkg("knn")
+    g = np.stack(np.meshgrid(np.arange(9.0), np.arange(9.0), np.arange(9.0), indexing="ij"), -1).reshape(-1, 3)
+    idx, dist = knn.knn(g, g, 7)
+    idx, dist = idx.cpu().numpy(), dist.cpu().numpy()
+    centre = 4 * 81 + 4 * 9 + 4
+    assert idx[centre, 0] == centre and np.allclose(dist[centre, 1:], 1.0)
+    assert list(idx[centre, 1:]) == sorted(idx[centre, 1:])           # six equidistant neighbours, ascending index
+
+
+def test_dropin_graph_prolongation_and_smoothing_match_reference_fixtures():
+    """utils.build_prolongation / build_knn_graph (GPU kNN underneath) and the device Jacobi sweeps against the
+    reference's own outputs."""
+    import sys
+    sys.modules.pop("utils", None)
+    utils = dropin("utils")
+    g, fem = load_golden("prep_cgc.npz"), load_golden("bunny_fem.npz")
+    n = fem["verts"].shape[0]
+    K, M = csr_from_golden(fem, "K", n), csr_from_golden(fem, "M", n)
+    P = utils.build_prolongation(fem["coarse_verts"], fem["verts"], k=8).tocsr()
+    Pref = sp.coo_matrix((g["P_data"], (g["P_row"], g["P_col"])), shape=P.shape).tocsr()
+    assert abs(P - Pref).max() < 1e-10
+    knn_g = utils.build_knn_graph(fem["coarse_verts"], k=5).numpy()
+    assert knn_g.shape == g["knn_coarse"].shape and np.array_equal(knn_g[0], g["knn_coarse"][0])
+    same = [set(knn_g[1, i * 5:(i + 1) * 5]) == set(g["knn_coarse"][1, i * 5:(i + 1) * 5]) for i in range(knn_g.shape[1] // 5)]
+    assert np.mean(same) > 0.999
+    U1 = utils.jacobi_smooth_device(M, K, P @ g["U0"], alpha=0.1, n_iters=10)
+    assert np.abs(U1 - g["U1"]).max() <= 2e-5 * np.abs(g["U1"]).max()
+    # device CSR prolongation applied with the SpMM kernel = scipy P @ U
+    knn, ops = pkg("knn"), pkg("ops")
+    Pd = knn.prolongation(fem["coarse_verts"], fem["verts"], 8)
+    U0 = torch.from_numpy(g["U0"].astype(np.float32)).to(dev())
+    np.testing.assert_allclose(ops.spmm(Pd, U0).cpu().numpy(), Pref @ g["U0"], rtol=1e-4, atol=1e-6)

@@ -309,11 +309,12 @@ def test_tensor_core_backward_equals_simt_backward():
         acc = torch.zeros(ops.N_LOSS_TERMS, dtype=torch.float64, device=dev())
         _, coef = ops.eigen_finalize(k, n, Pp, 1000.0, 10.0, acc, w_mean=2.0, w_smooth=1.5)
         outs = []
+        min_k, ops.TENSOR_CORE_GRAM_MIN_K = ops.TENSOR_CORE_GRAM_MIN_K, 16
         for tc in (False, True):
             ops.TENSOR_CORE_GRAM = tc
             d = torch.zeros(n, k, device=dev())
             ops.eigen_bwd_fused(pair, KU, MU, coef, 0.7, d, rows=(0, 1000))
             ops.eigen_bwd_fused(pair, KU, MU, coef, 0.7, d, rows=(1000, n))
             outs.append(d)
-        ops.TENSOR_CORE_GRAM = True
+        ops.TENSOR_CORE_GRAM, ops.TENSOR_CORE_GRAM_MIN_K = True, min_k
         assert (outs[0] - outs[1]).abs().max().item() <= 1e-5 * outs[0].abs().max().item()
