@@ -56,8 +56,18 @@ def test_dropin_graph_prolongation_and_smoothing_match_reference_fixtures():
     assert abs(P - Pref).max() < 1e-10
     knn_g = utils.build_knn_graph(fem["coarse_verts"], k=5).numpy()
     assert knn_g.shape == g["knn_coarse"].shape and np.array_equal(knn_g[0], g["knn_coarse"][0])
-    same = [set(knn_g[1, i * 5:(i + 1) * 5]) == set(g["knn_coarse"][1, i * 5:(i + 1) * 5]) for i in range(knn_g.shape[1] // 5)]
-    assert np.mean(same) > 0.999
+    # this decimated mesh is full of EXACTLY repeated edge lengths: wherever the 6th and 7th nearest distances differ
+    # the neighbour set must equal the reference's; where they tie (to the last bits) any of the tied points is a
+    # correct answer and the choice is implementation defined (sklearn's tree order vs smallest index here)
+    Xc = fem["coarse_verts"]
+    from sklearn.neighbors import NearestNeighbors
+    d7, _ = NearestNeighbors(n_neighbors=7).fit(Xc).kneighbors(Xc)
+    untied = (d7[:, 6] - d7[:, 5]) > 1e-9 * d7[:, 5]
+    same = np.array([set(knn_g[1, i * 5:(i + 1) * 5]) == set(g["knn_coarse"][1, i * 5:(i + 1) * 5])
+                     for i in range(knn_g.shape[1] // 5)])
+    assert untied.mean() > 0.8 and same[untied].all()
+    d_gpu = np.linalg.norm(Xc[knn_g[1]] - Xc[knn_g[0]], axis=1).reshape(-1, 5)
+    np.testing.assert_allclose(np.sort(d_gpu, axis=1), d7[:, 1:6], rtol=1e-12)      # same distances everywhere
     U1 = utils.jacobi_smooth_device(M, K, P @ g["U0"], alpha=0.1, n_iters=10)
     assert np.abs(U1 - g["U1"]).max() <= 2e-5 * np.abs(g["U1"]).max()
     # device CSR prolongation applied with the SpMM kernel = scipy P @ U
