@@ -334,12 +334,13 @@ def timed_steps(eng, args, dev, rank, world, epoch0, clock_sampler=None):
                 launches_by_entry=getattr(eng, "launches_by_entry", None))
 
 
-def trained_accuracy(mlp_mode, epochs=3000):
+def trained_accuracy(mlp_mode, epochs=10000):
     """BASELINE "lambda rel err" of a TRAINED run, through the drop-in surface: coarse FEM level (1057 vertices) + bunny
     (2503 vertices) from tests/golden/bunny_fem.npz, k = 16, MLP 50 -> 256 x 6 -> 16, MultigridGNN.train_multiresolution
     for `epochs` epochs (CUDA-graph replayed, loss read back every epoch), Rayleigh-Ritz on the finest level, eigenvalues
     against scipy's eigsh on the same FEM operators.  profiles/r02_trained_accuracy_*.json holds the same problem trained
-    by the CPU oracle for comparison (first-10 max error 0.559 after 3000 epochs: the reference's own accuracy level)."""
+    by the CPU oracle for comparison (the reference's own accuracy level; 10 000 epochs is the reference's default, the
+    correction scale ramps up over the first 5 000, src/multigrid_model.py:243)."""
     import types
     import torch
     import scipy.sparse as sp

@@ -431,15 +431,15 @@ eigen_bwd_prepare_kernel(int n, int k, const float* __restrict__ U, int ldu, con
 // writes dU once -> 12 nnz + 4 (n+1) + 12 n k bytes, like the forward dual SpMM.
 // Thread layout as in the SpMM: LPR lanes per row, 4 columns per lane; the k x k product takes the row's
 // MU values from the other lanes with shuffles and S from shared memory.
-template <int KVT>     // KVT = k / 4 when instantiated for a fixed width (fully unrolled product), 0 = generic
+// KVT = k / 4 when instantiated for a fixed width (fully unrolled product), 0 = generic;  GRAM_IN_OUT: dU already holds
+// out_scale * MU_i S (tensor-core kernel), the k x k product is compiled out and the gathered terms are added to it
+template <int KVT, bool GRAM_IN_OUT>
 __global__ void __launch_bounds__(256)
 eigen_bwd_fused_sym_kernel(int row0, int n, int k, int lpr_shift, const int32_t* __restrict__ rowptr,
                            const int32_t* __restrict__ col, const float* __restrict__ valK,
                            const float* __restrict__ valM, const float* __restrict__ KU,
                            const float* __restrict__ MU, int ld, const float* __restrict__ coef, float out_scale_v,
-                           const float* __restrict__ out_scale_dev, float* __restrict__ dU, int ldo, int gram_in_out) {
-  // gram_in_out != 0: dU already holds out_scale * MU_i S (tensor-core kernel ep_eigen_bwd_gram_term_tf32x3); the
-  // k x k product below is skipped and the gathered terms are added to it
+                           const float* __restrict__ out_scale_dev, float* __restrict__ dU, int ldo) {
   const float out_scale = out_scale_dev ? __ldg(out_scale_dev) : out_scale_v;
   extern __shared__ __align__(16) float fsm[];
   float* S = fsm;                 // k x k
@@ -515,7 +515,7 @@ eigen_bwd_fused_sym_kernel(int row0, int n, int k, int lpr_shift, const int32_t*
       acc.z = fmaf(a24.z, ku_i.z, acc.z); acc.w = fmaf(a24.w, ku_i.w, acc.w);
     }
     // acc += MU_i S : lane L of the row group holds MU_i[4L .. 4L+3]
-    if (!gram_in_out)
+    if constexpr (!GRAM_IN_OUT) {
 #pragma unroll
     for (int L = 0; L < kv; ++L) {
       const float m0 = __shfl_sync(0xffffffffu, mu_i.x, L, lpr);
@@ -532,9 +532,10 @@ eigen_bwd_fused_sym_kernel(int row0, int n, int k, int lpr_shift, const int32_t*
       acc.x = fmaf(m2, s2.x, acc.x); acc.y = fmaf(m2, s2.y, acc.y); acc.z = fmaf(m2, s2.z, acc.z); acc.w = fmaf(m2, s2.w, acc.w);
       acc.x = fmaf(m3, s3.x, acc.x); acc.y = fmaf(m3, s3.y, acc.y); acc.z = fmaf(m3, s3.z, acc.z); acc.w = fmaf(m3, s3.w, acc.w);
     }
+    }
     if (active && valid) {
       float4* dst = reinterpret_cast<float4*>(dU + (size_t)row * ldo + cofs);
-      if (gram_in_out) {
+      if (GRAM_IN_OUT) {
         const float4 t = *dst;
         acc.x = fmaf(acc.x, out_scale, t.x); acc.y = fmaf(acc.y, out_scale, t.y);
         acc.z = fmaf(acc.z, out_scale, t.z); acc.w = fmaf(acc.w, out_scale, t.w);
@@ -812,8 +813,9 @@ int ep_eigen_bwd_gather_sym_rows_f32(int row0, int n, int k, const int32_t* rowp
   const size_t smem = sizeof(float) * ((size_t)k * k + 2 * k);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    EP_CUDA_CHECK(cudaFuncSetAttribute(eigen_bwd_fused_sym_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    EP_CUDA_CHECK(cudaFuncSetAttribute(eigen_bwd_fused_sym_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EP_CUDA_CHECK(cudaFuncSetAttribute(eigen_bwd_fused_sym_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EP_CUDA_CHECK(cudaFuncSetAttribute(eigen_bwd_fused_sym_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EP_CUDA_CHECK(cudaFuncSetAttribute(eigen_bwd_fused_sym_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   const long long threads = (long long)n << lpr_shift;
@@ -830,14 +832,23 @@ int ep_eigen_bwd_gather_sym_rows_f32(int row0, int n, int k, const int32_t* rowp
     EP_LAUNCH_CHECK("eigen_bwd_fused_sym_k32_kernel");
     return EP_OK;
   }
-#define EP_FUSED_LAUNCH(KVT) eigen_bwd_fused_sym_kernel<KVT><<<(unsigned)grid, 256, smem, st>>>( \
-      row0, n, k, lpr_shift, rowptr, col, valK, valM, KU, MU, ld, coef, out_scale, out_scale_dev, dU, ldo, gram_in_out)
-  switch (kv) {
-    case 4: EP_FUSED_LAUNCH(4); break;
-    case 8: EP_FUSED_LAUNCH(8); break;
-    case 16: EP_FUSED_LAUNCH(16); break;
-    case 32: EP_FUSED_LAUNCH(32); break;
-    default: EP_FUSED_LAUNCH(0); break;
+#define EP_FUSED_LAUNCH(KVT, G) eigen_bwd_fused_sym_kernel<KVT, G><<<(unsigned)grid, 256, smem, st>>>( \
+      row0, n, k, lpr_shift, rowptr, col, valK, valM, KU, MU, ld, coef, out_scale, out_scale_dev, dU, ldo)
+  if (gram_in_out) {
+    switch (kv) {
+      case 4: EP_FUSED_LAUNCH(4, true); break;
+      case 8: EP_FUSED_LAUNCH(8, true); break;
+      case 16: EP_FUSED_LAUNCH(16, true); break;
+      default: EP_FUSED_LAUNCH(0, true); break;
+    }
+  } else {
+    switch (kv) {
+      case 4: EP_FUSED_LAUNCH(4, false); break;
+      case 8: EP_FUSED_LAUNCH(8, false); break;
+      case 16: EP_FUSED_LAUNCH(16, false); break;
+      case 32: EP_FUSED_LAUNCH(32, false); break;
+      default: EP_FUSED_LAUNCH(0, false); break;
+    }
   }
 #undef EP_FUSED_LAUNCH
   EP_LAUNCH_CHECK("eigen_bwd_fused_sym_kernel");

@@ -65,7 +65,7 @@ def test_dropin_graph_prolongation_and_smoothing_match_reference_fixtures():
     untied = (d7[:, 6] - d7[:, 5]) > 1e-9 * d7[:, 5]
     same = np.array([set(knn_g[1, i * 5:(i + 1) * 5]) == set(g["knn_coarse"][1, i * 5:(i + 1) * 5])
                      for i in range(knn_g.shape[1] // 5)])
-    assert untied.mean() > 0.8 and same[untied].all()
+    assert untied.mean() > 0.3 and same[untied].all()          # (more than half of this mesh's vertices have such ties)
     d_gpu = np.linalg.norm(Xc[knn_g[1]] - Xc[knn_g[0]], axis=1).reshape(-1, 5)
     np.testing.assert_allclose(np.sort(d_gpu, axis=1), d7[:, 1:6], rtol=1e-12)      # same distances everywhere
     U1 = utils.jacobi_smooth_device(M, K, P @ g["U0"], alpha=0.1, n_iters=10)
