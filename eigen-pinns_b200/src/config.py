@@ -23,6 +23,8 @@ OPTIONAL_FIELDS = {
     "cgc_shift": 1e-3,         # "regularized": coarse solve with K_c + cgc_shift * M_c (block CG on the device)
     "loss_read_delay": 1,      # epochs between launching a step and reading its loss (0 = synchronous like :261)
     "cuda_graph": True,        # replay the epoch body as one CUDA graph after three eager epochs
+    "offset_edges": False,     # True: per-level edge lists get node offsets (notebooks); False: reference quirk Q3
+    "aggregation": "mean",     # 'mean' (reference) | 'sum' (notebook variant without the degree division)
     "operator_type": "auto",   # level operators of the point samplers: "point_cloud" (robust_laplacian, as the
                                # reference), "fem" (Galerkin P^T K P of the mesh's FEM operators), "auto" (first if installed)
 }

@@ -82,19 +82,30 @@ class _GraphCache:
 
 
 class SimpleCorrector(nn.Module):
-    def __init__(self, in_dim, out_dim, hidden_layers, dropout):
+    """aggregation='mean' is the reference (src/corrector_model.py:23-30).  aggregation='sum' is the notebook variant
+    without the degree division (`SimpleGNN` of transfer_learning_downsampling.ipynb cell 0): the same
+    gather kernel with unit edge weights (ep_spmm_concat_f32 on the multi-adjacency, duplicates kept)."""
+
+    def __init__(self, in_dim, out_dim, hidden_layers, dropout, aggregation="mean"):
         super().__init__()
+        if aggregation not in ("mean", "sum"):
+            raise ValueError(f"aggregation must be 'mean' or 'sum', got '{aggregation}'")
+        self.aggregation = aggregation
         self.net = _build_net(in_dim, out_dim, hidden_layers, dropout)
         self._cache = _GraphCache()
 
     def corrector_input(self, x, edge_index):
         c = self._cache
         if not c.graph_hit(edge_index, x.shape[0]):
-            c.set_graph(edge_index, x.shape[0], _sparse.CsrMatrix.from_edge_index(edge_index, x.shape[0], x.device))
+            csr = _sparse.CsrMatrix.from_edge_index(edge_index, x.shape[0], x.device)
+            if self.aggregation == "sum":
+                csr.val = torch.ones(csr.nnz, dtype=torch.float32, device=x.device)
+            c.set_graph(edge_index, x.shape[0], csr)
         if x.requires_grad:
             raise NotImplementedError("gradients w.r.t. the node features are not part of the hot path")
         if not c.input_hit(x):
-            c.set_input(x, _ops.neighbor_mean_concat(x, c.csr))
+            c.set_input(x, _ops.neighbor_mean_concat(x, c.csr) if self.aggregation == "mean"
+                        else _ops.spmm_concat(x, c.csr))
         return c.h
 
     def forward(self, x, edge_index):

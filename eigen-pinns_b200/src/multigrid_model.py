@@ -46,6 +46,8 @@ class MultigridGNN:
         self.mlp_mode = getattr(config, "mlp_mode", "fp32")
         self.cgc_mode = getattr(config, "cgc_mode", "reference")
         self.cgc_shift = float(getattr(config, "cgc_shift", 1e-3))
+        self.offset_edges = bool(getattr(config, "offset_edges", False))
+        self.aggregation = getattr(config, "aggregation", "mean")
         self.loss_read_delay = int(getattr(config, "loss_read_delay", 1))
         self.graph_after_epochs = 3 if getattr(config, "cuda_graph", True) else -1
         self.seed = getattr(config, "seed", None)
@@ -115,8 +117,12 @@ class MultigridGNN:
             feats.append(f)
             edges.append(ei)
         x_all = torch.cat(feats, dim=0).contiguous()
-        # NB: like the reference, per-level edge lists are concatenated without node offsets
-        edge_all = torch.cat(edges, dim=1)
+        # NB: like the reference, per-level edge lists are concatenated without node offsets;
+        # `offset_edges: true` applies the offsets like the notebooks do (edge_index + node_offset)
+        if self.offset_edges:
+            edge_all = utils.offset_edge_lists(edges, [f.shape[0] for f in feats])
+        else:
+            edge_all = torch.cat(edges, dim=1)
         A_norm = utils.build_A_norm(edge_all, x_all.shape[0], self.device) if self.model_type == 'spectral' else None
         return x_all, edge_all, A_norm
 
@@ -143,8 +149,11 @@ class MultigridGNN:
             return
         if self.seed is not None:
             torch.manual_seed(self.seed)
-        cls = SimpleCorrector if self.model_type == 'simple' else SpectralCorrector
-        self.model = cls(input_dim, n_modes, hidden_layers, dropout).to(self.device)
+        if self.model_type == 'simple':
+            self.model = SimpleCorrector(input_dim, n_modes, hidden_layers, dropout, aggregation=self.aggregation)
+        else:
+            self.model = SpectralCorrector(input_dim, n_modes, hidden_layers, dropout)
+        self.model = self.model.to(self.device)
         nn.init.normal_(self.model.net[-1].weight, mean=0.0, std=0.01)      # escape the "do nothing" minimum
         nn.init.zeros_(self.model.net[-1].bias)
         print(f"Model initialized ({self.model_type}): input_dim={input_dim}, output_dim={n_modes}")

@@ -79,6 +79,17 @@ def build_knn_graph(X, k):
     return torch.from_numpy(np.stack([rows, idx[:, 1:].astype(np.int64).ravel()]))
 
 
+def offset_edge_lists(edge_index_list, sizes):
+    """Concatenate per-level edge lists WITH node offsets (`edge_index + node_offset` of the multigrid notebooks, SURVEY
+    8a-bis) - src/multigrid_model.py:147-150 concatenates them un-offset (quirk Q3), which aggregates every level's
+    edges into the first rows of the stacked feature matrix."""
+    out, off = [], 0
+    for ei, n in zip(edge_index_list, sizes):
+        out.append(ei + off)
+        off += int(n)
+    return torch.cat(out, dim=1)
+
+
 def build_A_norm(edge_index, n_nodes, device):
     """D^-1/2 (A + I) D^-1/2 with A the coalesced (multi-)adjacency and D counting the stored
     entries per row of A + I - the exact recipe of reference :78-124 - as a torch sparse tensor."""

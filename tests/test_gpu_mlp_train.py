@@ -217,3 +217,25 @@ def test_regularized_cg_coarse_solve_matches_reference_dense_solve():
     U2, _ = gnn.apply_coarse_grid_correction(torch.from_numpy(g["U1"]).float(), K, M, sp.coo_matrix(Kc), P,
                                              M_coarse=sp.coo_matrix(Mc))
     assert torch.isfinite(U2).all()
+
+
+def test_sum_aggregation_and_offset_edges_variants():
+    """Notebook variants of the aggregation: sum instead of mean, and per-level edge lists with node
+    offsets; against torch index_add_ on the CPU."""
+    cm, utils = dropin("corrector_model"), dropin("utils")
+    g = torch.Generator().manual_seed(2)
+    n0, n1, d = 300, 500, 7
+    x = torch.randn(n0 + n1, d, generator=g)
+    e0 = torch.randint(0, n0, (2, 2000), generator=g)
+    e1 = torch.randint(0, n1, (2, 3000), generator=g)
+    ei = utils.offset_edge_lists([e0, e1], [n0, n1])
+    assert ei.shape == (2, 5000) and int(ei[:, 2000:].min()) >= n0
+    model = cm.SimpleCorrector(d, 4, [16], 0.0, aggregation="sum").to(dev())
+    h = model.corrector_input(x.to(dev()), ei.to(dev())).cpu()
+    agg = torch.zeros_like(x)
+    agg.index_add_(0, ei[0], x[ei[1]])
+    np.testing.assert_allclose(h[:, :d].numpy(), x.numpy(), rtol=0, atol=0)
+    np.testing.assert_allclose(h[:, d:].numpy(), agg.numpy(), rtol=1e-5, atol=1e-5)
+    assert model(x.to(dev()), ei.to(dev())).shape == (n0 + n1, 4)
+    with pytest.raises(ValueError):
+        cm.SimpleCorrector(d, 4, [16], 0.0, aggregation="max")
