@@ -36,9 +36,9 @@ WORKLOADS = {
 }
 HIDDEN = [256] * 6                               # reference default (src/parameters.yml)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch / vertices from the committed ncu --set full captures
-# (profiles/r02_ncu_chain_summary.csv: tc_chain_kernel<FWD> 0.3313 GB + 3.3329 GB at 998,562 vertices, k = 32;
+# (profiles/r02_ncu_chain2_summary.csv: tc_chain2_kernel<FWD> 0.3244 GB + 3.3339 GB at 998,562 vertices, k = 32;
 #  profiles/r01_final_ncu_full_summary.csv: spmm_kernel<4,1> 0.4330 GB)
-NCU_TRAFFIC_CHAIN_FWD_PER_VERTEX = (0.331345e9 + 3.332921e9) / 998562
+NCU_TRAFFIC_CHAIN_FWD_PER_VERTEX = (0.324381e9 + 3.333947e9) / 998562
 NCU_TRAFFIC_SPMM2_PER_VERTEX = 0.4330e9 / 998562
 MIN_TIMED_MS = 1000.0                            # every timed region lasts at least this long (clock sampling, sustained rates)
 
@@ -579,8 +579,9 @@ def run_ours(args):
     if chain_ms is not None:
         gbs = chain_bytes / (chain_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm",
-                    "kernel": "tc_chain_kernel<FWD> (tcgen05: all %d layers of the corrector for a pair of 128-vertex tiles per "
-                              "persistent CTA; activations + ReLU masks streamed to HBM once, never read back)" % eng_layers(d_in, k),
+                    "kernel": "tc_chain2_kernel<FWD> (tcgen05 cta_group::2: all %d layers of the corrector, persistent CTA pairs, two "
+                              "128-vertex tiles per CTA in ping-pong; activations + ReLU masks streamed to HBM once, never read "
+                              "back)" % eng_layers(d_in, k),
                     "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
                     "traffic": NCU_TRAFFIC_CHAIN_FWD_PER_VERTEX * n_loc,
                     "peak_source": peaks["source"] + " hbm copy (kernel timed alone)", "ms": chain_ms,

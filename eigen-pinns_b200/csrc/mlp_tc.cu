@@ -522,6 +522,391 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_kernel(const __grid_co
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
+// ------------------------------------------------------------------------------------------- layer chain, CTA pairs
+// tc_chain2_kernel: the same layer chain, run by CLUSTERS OF TWO CTAs with tcgen05.mma.cta_group::2.
+// What the single-CTA kernel cannot do is overlap the MMAs of one tile with the drain of another: both TMEM accumulators
+// and all shared memory that the weights leave belong to the tile pair in flight.  A CTA pair changes the budget:
+//   * one MMA covers M = 256 rows, 128 from each CTA's operand tile, and the hardware takes HALF of the B operand from
+//     each CTA's shared memory: a CTA stores only its N/2 output columns of every weight slab (8 KB instead of 16 KB per
+//     K = 32), so a ring of 80 KB holds a whole layer (64 KB) and each CTA streams every layer ONCE per two tiles;
+//   * a CTA therefore works on two tiles of its own in ping-pong ("slots" P and Q, one 64 KB operand tile and one
+//     256-column accumulator each): while the pair's tensor cores run layer l of slot Q, all eight epilogue warps of
+//     each CTA drain layer l of slot P and write the operand of layer l + 1 - and vice versa.  Both slots use the same
+//     ring slots of layer l (P is their first reader, Q releases them).
+// Barriers (rank 0 = leader, issues every MMA; counts in brackets: leader / peer):
+//   wempty[s]     [1/1]      tcgen05.commit.cta_group::2 ... multicast: the pair's MMAs that read ring slot s have retired
+//   landed[l & 1] [4/3]      all weight slabs of one layer are in this CTA's ring: one arrive.expect_tx per producer
+//                            warp with the bytes of its slabs, complete_tx by every slab copy; leader: + one remote
+//                            arrive by the peer
+//   in_full[u]    [2/1]      input tile of slot u has landed; leader: + one remote arrive by the peer
+//   acc_full[u]   [1/1]      commit multicast: all MMAs of one layer of slot u have retired -> epilogues of both CTAs
+//   act_ready[u]  [512/-]    every epilogue thread of BOTH CTAs has drained its part of the accumulator and written +
+//                            fenced its part of the next operand (the peer's threads arrive remotely)
+// The peer forwards `landed` and `in_full` with one thread (warp 1, otherwise idle there).  Learned the hard
+// way (tools/chain2_check.py traces): (1) a remote arrive with .release.cluster semantics from the 256 epilogue threads
+// costs ~2000 clk per step - it waits for the thread's outstanding HBM stores; the default semantics do not, and the
+// operand tile is fenced into the async proxy before the arrive anyway; (2) every mbarrier try_wait in the
+// MMA-issuing thread costs ~250 clk while the tensor pipe saturates shared memory, so a wait per weight slab (16 per
+// layer) starves the tensor pipe (360 instead of 130 clk per MMA) - hence one barrier per LAYER and merged counts: the
+// MMA thread waits for at most three barriers per (layer, slot) step and then issues 16 MMAs back to back.
+// Weight slabs come from the second, "pair" copy of the packed weights ([K/32][half][4][N/2][8], see pack_weight_kernel):
+// a CTA's half of a slab is one contiguous bulk copy; three warps take turns issuing them (a thread sustains one
+// cp.async.bulk round per ~635 clk whatever its size, tools/micro/bulk_bw.cu).
+// Work: cluster c takes units c, c + n_clusters, ...; unit = tiles (2 unit, 2 unit + 1), one per CTA.
+// Measured (B200, 998,562 rows, 82->256x6->32): forward 0.99 ms against 1.08 ms for the single-CTA kernel, dZ chain
+// 0.76 against 0.80 ms, bit-identical outputs.  Per 256-wide layer and CTA (two tiles): ~7800 clk against 10100; the
+// tensor pipe is busy 34 % of the time (ncu, profiles/r02_ncu_chain2_summary.csv).  What bounds it now is the drain:
+// 2600-3500 clk per 128 x 256 tile whether 8 or 16 warps do it, with or without the TMEM load of the next block in
+// flight - the L1 / shared-memory data pipe carries 1400 wavefronts per tile for the epilogue (64 KB st.shared + 64 KB
+// st.global + bias reads) plus 1024 for the MMA operands of the other slot (69 % busy over the kernel).
+constexpr int C2_PRODUCERS = 3;               // weight-issuing warps: 0, 10, 11
+constexpr int C2_THREADS = 384;               // + warp 1: MMA issuer (leader) / forwarder (peer), warps 2..9: epilogue.
+                                              // Twelve warps = three per scheduler = up to 168 registers; a 13th caps at 128.
+constexpr int C2_STAGES = 10;
+constexpr int C2_SLOT_BYTES = 8192;           // K = 32 rows x 128 columns (this CTA's half of a 256-wide slab)
+constexpr int C2_N_BARRIERS = C2_STAGES + 8;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(const void* smem_ptr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(smem_ptr)), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_pair(uint64_t* bar) {     // arrives at this offset in BOTH CTAs
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* slot_in_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(cols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
+}
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C2_THREADS, 1)
+tc_chain2_kernel(const __grid_constant__ ChainArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* act0 = smem;                                   // operand tile of slot P
+  uint8_t* act1 = smem + CH_ACT_BYTES;                    // operand tile of slot Q
+  uint8_t* ring = smem + 2 * CH_ACT_BYTES;
+  float* bias_s = reinterpret_cast<float*>(ring + C2_STAGES * C2_SLOT_BYTES);          // [CH_MAX_LAYERS][256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + CH_MAX_LAYERS * 256);
+  uint64_t* wempty = bars;                         // [C2_STAGES]
+  uint64_t* landed = wempty + C2_STAGES;           // [2]
+  uint64_t* in_full = landed + 2;                  // [2]
+  uint64_t* acc_full = in_full + 2;                // [2]
+  uint64_t* act_ready = acc_full + 2;              // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C2_N_BARRIERS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = a.n_layers;
+  const int rank = (int)cluster_ctarank();
+  const bool leader = rank == 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C2_STAGES; ++s) mbar_init(&wempty[s], 1);
+    for (int u = 0; u < 2; ++u) {
+      mbar_init(&landed[u], C2_PRODUCERS + (leader ? 1 : 0));
+      mbar_init(&in_full[u], leader ? 2 : 1);
+      mbar_init(&acc_full[u], 1);
+      mbar_init(&act_ready[u], 512);
+    }
+    fence_barrier_init();
+  }
+  if (MODE == MODE_CHAIN_FWD) {
+    for (int i = threadIdx.x; i < L * 256; i += blockDim.x) {
+      const int l = i >> 8, c = i & 255;
+      bias_s[i] = (a.L[l].bias && c < a.L[l].n_bias) ? a.L[l].bias[c] : 0.f;
+    }
+  }
+  if (warp == 1) tmem_alloc2(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                 // both CTAs' barriers and TMEM exist before anything crosses over
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_units = (a.n_tiles + 1) >> 1;
+  const int n_clusters = (int)gridDim.x >> 1;
+  const int cluster_id = (int)blockIdx.x >> 1;
+  const int my_units = cluster_id < n_units ? (n_units - cluster_id + n_clusters - 1) / n_clusters : 0;
+  auto unit_of = [&](int j) { return cluster_id + j * n_clusters; };
+  const uint32_t in_bytes = (uint32_t)a.L[0].KC * CHUNK_BYTES;
+
+  if (warp == 0 || warp >= 10) {
+    // ---- weights: this CTA's N/2 output columns of every K = 32 slab, each layer once per unit pair; the slabs of the
+    //      whole sequence are dealt round-robin to the C2_PRODUCERS issuing warps
+    if (lane == 0) {
+      const int me = warp == 0 ? 0 : warp - 9;
+      uint32_t gs = 0;                               // slab counter over the whole sequence
+      uint32_t lc = 0;                               // layer counter over the whole sequence
+      for (int j = 0; j < my_units; j += 2) {
+        for (int l = 0; l < L; ++l, ++lc) {
+          const int N = a.L[l].N;
+          const uint32_t half_bytes = (uint32_t)(N >> 1) * 64u;          // 4 chunks x N/2 columns x 16 B
+          const int n_slabs = a.L[l].KC >> 2;
+          const uint8_t* src = a.L[l].B + (size_t)a.L[l].KC * N * 16 + (size_t)rank * half_bytes;    // the "pair" copy
+          // Every producer announces the bytes of ITS slabs of this layer with one arrive.expect_tx (so the transaction
+          // count never goes negative) - after the barrier's previous phase (layer lc - 2) is complete.
+          {
+            int mine = 0;
+            for (int s = 0; s < n_slabs; ++s) mine += ((gs + s) % C2_PRODUCERS) == (uint32_t)me ? 1 : 0;
+            if (lc >= 2) mbar_wait(&landed[lc & 1], ((lc - 2) >> 1) & 1);
+            if (mine) mbar_expect_tx(&landed[lc & 1], (uint32_t)mine * half_bytes);
+            else mbar_arrive(&landed[lc & 1]);
+          }
+          for (int s = 0; s < n_slabs; ++s, ++gs) {
+            if ((int)(gs % C2_PRODUCERS) != me) continue;
+            const uint32_t stage = gs % C2_STAGES, phase = (gs / C2_STAGES) & 1;
+            mbar_wait(&wempty[stage], phase ^ 1);
+            bulk_g2s(ring + stage * C2_SLOT_BYTES, src + (size_t)s * 2 * half_bytes, half_bytes, &landed[lc & 1]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && !leader) {
+      // ---- peer: tell the leader when a layer's weights / the input tile of a slot have landed here (or that there is
+      //      no tile); the two event streams interleave, so poll both
+      const uint32_t remote_w[2] = {map_to_cta(&landed[0], 0), map_to_cta(&landed[1], 0)};
+      const uint32_t remote_i[2] = {map_to_cta(&in_full[0], 0), map_to_cta(&in_full[1], 0)};
+      const uint32_t n_layers_total = (uint32_t)((my_units + 1) >> 1) * (uint32_t)L;
+      uint32_t lc = 0, nu[2] = {0, 0};
+      int j = 0;
+      for (uint32_t spin = 0; lc < n_layers_total || j < my_units; ++spin) {
+        if (lc < n_layers_total && mbar_test(&landed[lc & 1], (lc >> 1) & 1)) { mbar_arrive_remote(remote_w[lc & 1]); ++lc; spin = 0; }
+        if (j < my_units) {
+          const int u = j & 1;
+          if (2 * unit_of(j) + rank >= a.n_tiles || mbar_test(&in_full[u], nu[u] & 1)) {
+            mbar_arrive_remote(remote_i[u]); ++nu[u]; ++j; spin = 0;
+          }
+        }
+        if (spin > (1u << 28)) { printf("eigenpinns_b200: forwarder timed out (block %d)\n", blockIdx.x); __trap(); }
+      }
+    } else if (lane == 0) {
+      // ---- leader: every MMA of the pair
+      uint32_t stage = 0;
+      uint32_t lc = 0;
+      uint32_t gl[2] = {0, 0};                       // layers completed per slot
+      uint32_t nu[2] = {0, 0};                       // units started per slot
+      const uint32_t abase[2] = {smem_u32(act0), smem_u32(act1)};
+      for (int j = 0; j < my_units; j += 2) {
+        const bool has_q = (j + 1) < my_units;
+        for (int l = 0; l < L; ++l, ++lc) {
+          const int N = a.L[l].N;
+          const uint32_t idesc = make_idesc(256, N, false, false);
+          const uint32_t b_lbo = (uint32_t)(N >> 1) * 16;
+          const int n_slabs = a.L[l].KC >> 2;
+          for (int u = 0; u < (has_q ? 2 : 1); ++u) {
+            if (l == 0) mbar_wait_spin(&in_full[u], nu[u] & 1);
+            if (u == 0) mbar_wait_spin(&landed[lc & 1], (lc >> 1) & 1);
+            if (gl[u] > 0) mbar_wait_spin(&act_ready[u], (gl[u] - 1) & 1);
+            tc_fence_after();
+            const uint32_t tg = gl[0] + gl[1];
+            if (a.trace && blockIdx.x == 0 && tg < 64) a.trace[tg * 8 + 0] = clock64();      // operands ready
+            const bool releases = (u == 1) || !has_q;       // last reader of the layer's slots
+            for (int s = 0; s < n_slabs; ++s) {
+              uint32_t slot = stage + s;
+              if (slot >= C2_STAGES) slot -= C2_STAGES;
+              const uint32_t b_base = smem_u32(ring + slot * C2_SLOT_BYTES);
+#pragma unroll
+              for (int jj = 0; jj < 2; ++jj) {
+                const uint64_t bdesc = make_desc(b_base + (uint32_t)(jj * 2) * b_lbo, b_lbo, 128);
+                const uint64_t adesc = make_desc(abase[u] + (uint32_t)(s * 4 + jj * 2) * CHUNK_BYTES, CHUNK_BYTES, 128);
+                umma2_bf16(tmem_base + (uint32_t)u * 256u, adesc, bdesc, idesc, (s | jj) != 0 ? 1u : 0u);
+              }
+              if (releases) umma2_commit_pair(&wempty[slot]);
+            }
+            umma2_commit_pair(&acc_full[u]);
+            if (a.trace && blockIdx.x == 0 && tg < 64) a.trace[tg * 8 + 1] = clock64();      // all MMAs issued
+            ++gl[u];
+          }
+          stage += n_slabs;
+          if (stage >= C2_STAGES) stage -= C2_STAGES;
+        }
+        ++nu[0]; ++nu[1];
+      }
+    }
+  } else {
+    // ---- epilogue: 8 warps on ONE tile (slot u of the current step); TMEM lane quadrant q, column half hf
+    const int q = warp & 3;
+    const int hf = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const bool elected = (warp == 2 && lane == 0);
+    const uint32_t ready_remote[2] = {map_to_cta(&act_ready[0], 0), map_to_cta(&act_ready[1], 0)};
+    auto issue_input = [&](int j) {                    // input tile of this CTA for its j-th unit -> slot j & 1
+      const int u = j & 1;
+      const int tile = 2 * unit_of(j) + rank;
+      if (tile < a.n_tiles) {
+        mbar_expect_tx(&in_full[u], in_bytes);
+        bulk_g2s(u ? act1 : act0, a.A0 + (size_t)tile * in_bytes, in_bytes, &in_full[u]);
+      }
+    };
+    if (elected) { if (my_units > 0) issue_input(0); if (my_units > 1) issue_input(1); }
+    const float scale = (MODE == MODE_CHAIN_FWD && a.scale_dev) ? *a.scale_dev : a.scale;
+    const bool vec_out = ((a.ldc | a.ldu | a.n_out) & 3) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(a.corr) | reinterpret_cast<uintptr_t>(a.U_base) |
+                           reinterpret_cast<uintptr_t>(a.U_pred)) & 15u) == 0;
+    uint32_t gl[2] = {0, 0};
+    for (int j = 0; j < my_units; j += 2) {
+      const bool has_q = (j + 1) < my_units;
+      for (int l = 0; l < L; ++l) {
+        const int N = a.L[l].N, ncb = N >> 5;
+        const int my_cb = min(4, ncb - 4 * hf);           // 32-column blocks of this warp (<= 0: none)
+        uint8_t* const out_packed = a.L[l].out_packed;
+        uint32_t* const mask_ptr = a.L[l].mask;
+        const float* bl = bias_s + l * 256 + hf * 128;
+        const bool last = (l == L - 1);
+        for (int u = 0; u < (has_q ? 2 : 1); ++u) {
+          const int tile = 2 * unit_of(j + u) + rank;
+          const bool valid = tile < a.n_tiles;
+          const bool work = valid && my_cb > 0;
+          const long long row = (long long)tile * TILE_M + r;
+          uint8_t* act = u ? act1 : act0;
+          const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)u * 256u + (uint32_t)hf * 128u;
+          uint32_t mw[4];
+          float4 ub[8];
+          if (MODE == MODE_CHAIN_DX && work) {
+            const uint32_t* mrow = mask_ptr + (size_t)row * ncb + 4 * hf;
+            if (my_cb == 4) {
+              const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mrow));
+              mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w;
+            } else {
+#pragma unroll
+              for (int w = 0; w < 4; ++w) mw[w] = w < my_cb ? __ldg(mrow + w) : 0u;
+            }
+          }
+          const bool final_rows = MODE == MODE_CHAIN_FWD && last && work && row < a.n_rows;
+          if (final_rows && vec_out && a.U_pred) {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const int col = hf * 128 + 4 * jj;
+              ub[jj] = col < a.n_out ? __ldg(reinterpret_cast<const float4*>(a.U_base + (size_t)row * a.ldu + col))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          mbar_wait(&acc_full[u], gl[u] & 1);
+          tc_fence_after();
+          const uint32_t tg = gl[0] + gl[1];
+          if (a.trace && blockIdx.x == 0 && tg < 64 && threadIdx.x == 64) a.trace[tg * 8 + 2] = clock64();   // accumulator ready
+          if (last && elected && (j + u + 2) < my_units) issue_input(j + u + 2);     // slot u's operand tile is free
+          if (work) {
+            if (MODE == MODE_CHAIN_FWD && last) {
+              const bool in_rows = row < a.n_rows;
+              for (int cb = 0; cb < my_cb; ++cb) {
+                const int col0 = hf * 128 + cb * 32;
+                if (cb > 0 && vec_out && in_rows && a.U_pred) {
+#pragma unroll
+                  for (int jj = 0; jj < 8; ++jj) {
+                    const int col = col0 + 4 * jj;
+                    ub[jj] = col < a.n_out ? __ldg(reinterpret_cast<const float4*>(a.U_base + (size_t)row * a.ldu + col))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                  }
+                }
+                uint32_t v[32];
+                tmem_ld32(t_addr + cb * 32, v);
+                if (in_rows) {
+                  if (vec_out) {
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                      const int col = col0 + 4 * jj;
+                      if (col < a.n_out) {
+                        const float4 bj = *reinterpret_cast<const float4*>(bl + cb * 32 + 4 * jj);
+                        float4 c;
+                        c.x = __uint_as_float(v[4 * jj]) + bj.x;     c.y = __uint_as_float(v[4 * jj + 1]) + bj.y;
+                        c.z = __uint_as_float(v[4 * jj + 2]) + bj.z; c.w = __uint_as_float(v[4 * jj + 3]) + bj.w;
+                        if (a.corr) *reinterpret_cast<float4*>(a.corr + (size_t)row * a.ldc + col) = c;
+                        if (a.U_pred) {
+                          float4 uu;
+                          uu.x = __fadd_rn(ub[jj].x, __fmul_rn(scale, c.x)); uu.y = __fadd_rn(ub[jj].y, __fmul_rn(scale, c.y));
+                          uu.z = __fadd_rn(ub[jj].z, __fmul_rn(scale, c.z)); uu.w = __fadd_rn(ub[jj].w, __fmul_rn(scale, c.w));
+                          *reinterpret_cast<float4*>(a.U_pred + (size_t)row * a.ldu + col) = uu;
+                        }
+                      }
+                    }
+                  } else {
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) {
+                      const int col = col0 + jj;
+                      if (col < a.n_out) {
+                        const float c = __uint_as_float(v[jj]) + bl[cb * 32 + jj];
+                        if (a.corr) a.corr[(size_t)row * a.ldc + col] = c;
+                        if (a.U_pred)
+                          a.U_pred[(size_t)row * a.ldu + col] =
+                              __fadd_rn(__ldg(a.U_base + (size_t)row * a.ldu + col), __fmul_rn(scale, c));
+                      }
+                    }
+                  }
+                }
+              }
+            } else {
+              const size_t tile_off = (size_t)tile * (N >> 3) * CHUNK_BYTES + (size_t)r * 16;
+              const bool to_smem = !last;
+              uint32_t bits[4];
+              uint32_t va[32], vb[32];                     // two accumulator blocks: the load of block cb + 1 flies
+              tmem_ld32_issue(t_addr, va);                 // while block cb is converted and stored
+#pragma unroll
+              for (int cb = 0; cb < 4; ++cb) {
+                if (cb < my_cb) {
+                  uint32_t (&v)[32] = (cb & 1) ? vb : va;
+                  tmem_ld32_wait(v);
+                  if (cb + 1 < my_cb) tmem_ld32_issue(t_addr + (cb + 1) * 32, (cb & 1) ? va : vb);
+                  uint32_t w[16];
+                  if (MODE == MODE_CHAIN_FWD) bits[cb] = epi_block_fwd_sb(v, bl + cb * 32, w);
+                  else epi_block_dx(v, mw[cb], w);
+#pragma unroll
+                  for (int g4 = 0; g4 < 4; ++g4) {
+                    const uint4 o = make_uint4(w[4 * g4], w[4 * g4 + 1], w[4 * g4 + 2], w[4 * g4 + 3]);
+                    const size_t c_off = (size_t)((hf * 4 + cb) * 4 + g4) * CHUNK_BYTES;
+                    if (to_smem) *reinterpret_cast<uint4*>(act + c_off + (size_t)r * 16) = o;
+                    if (out_packed) *reinterpret_cast<uint4*>(out_packed + tile_off + c_off) = o;
+                  }
+                } else if (MODE == MODE_CHAIN_FWD) {
+                  bits[cb] = 0u;
+                }
+              }
+              if (MODE == MODE_CHAIN_FWD && mask_ptr) {
+                uint32_t* mrow = mask_ptr + (size_t)row * ncb + 4 * hf;
+                if (my_cb == 4) {
+                  *reinterpret_cast<uint4*>(mrow) = make_uint4(bits[0], bits[1], bits[2], bits[3]);
+                } else {
+#pragma unroll
+                  for (int cb = 0; cb < 4; ++cb) if (cb < my_cb) mrow[cb] = bits[cb];
+                }
+              }
+            }
+          }
+          if (a.trace && blockIdx.x == 0 && tg < 64 && threadIdx.x == 64) a.trace[tg * 8 + 3] = clock64();   // drained
+          if (!last) fence_proxy_async_smem();           // generic-proxy writes -> visible to the tensor core of this SM
+          tc_fence_before();
+          mbar_arrive_remote(ready_remote[u]);         // the leader's barrier, whichever CTA this is
+          if (a.trace && blockIdx.x == 0 && tg < 64 && threadIdx.x == 64) a.trace[tg * 8 + 4] = clock64();   // arrived
+          ++gl[u];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                 // neither CTA leaves (or frees TMEM) while the other may still signal it
+  if (warp == 1) { tc_fence_after(); tmem_dealloc2(tmem_base, TMEM_COLS); }
+}
+
 // ------------------------------------------------------------------------------------------- dW
 constexpr int DW_THREADS = 192;
 constexpr int DW_XSTAGES = 3;          // half tiles of X: 16 chunks = 32 KB
@@ -771,10 +1156,13 @@ pack_rows_kernel(int n, int d, int dp, const float* __restrict__ X, int ldx, uin
   }
 }
 
-// W fp32 [out x in] -> Wp [inp/8][outp][8] (B operand of the forward GEMM) and WTp [outp/8][inp][8] (dX GEMM)
+// W fp32 [out x in] -> Wp [inp/8][outp][8] (B operand of the forward GEMM) and WTp [outp/8][inp][8] (dX GEMM), each
+// followed by a second copy in the layout of the CTA-pair chain kernel: [K/32 slabs][half of N][4 chunks][N/2][8], so that
+// the N/2 columns one CTA of a pair needs of a K = 32 slab are contiguous (K = in, N = out for Wp; K = out, N = in for WTp).
+constexpr int W_REPLICAS = 2;
 __global__ void __launch_bounds__(256)
 pack_weight_kernel(int out, int in, int outp, int inp, const float* __restrict__ W, __nv_bfloat16* __restrict__ Wp,
-                   __nv_bfloat16* __restrict__ WTp) {
+                   __nv_bfloat16* __restrict__ WTp, bool pair_copy) {
   const int total = outp * inp;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int o = e / inp, i = e - o * inp;
@@ -782,6 +1170,16 @@ pack_weight_kernel(int out, int in, int outp, int inp, const float* __restrict__
     const __nv_bfloat16 b = __float2bfloat16_rn(w);
     Wp[(size_t)(i >> 3) * outp * 8 + (size_t)o * 8 + (i & 7)] = b;
     if (WTp) WTp[(size_t)(o >> 3) * inp * 8 + (size_t)i * 8 + (o & 7)] = b;
+    if (pair_copy) {
+      {
+        const int kc = i >> 3, nh = outp >> 1, half = o >= nh ? 1 : 0;
+        Wp[(size_t)total + ((size_t)(((kc >> 2) * 2 + half) * 4 + (kc & 3)) * nh + (o - half * nh)) * 8 + (i & 7)] = b;
+      }
+      if (WTp) {
+        const int kc = o >> 3, nh = inp >> 1, half = i >= nh ? 1 : 0;
+        WTp[(size_t)total + ((size_t)(((kc >> 2) * 2 + half) * 4 + (kc & 3)) * nh + (i - half * nh)) * 8 + (o & 7)] = b;
+      }
+    }
   }
 }
 
@@ -824,6 +1222,22 @@ int launch_chain(const ChainArgs& a, cudaStream_t st) {
   }
   const int n_pairs = (a.n_tiles + 1) / 2;
   ChainArgs b = a;
+  if (ep::tune_flag(6) == 0) {
+    // default: CTA pairs (tcgen05 cta_group::2), one cluster of two per unit of two tiles
+    const size_t smem2 = 2 * (size_t)CH_ACT_BYTES + (size_t)C2_STAGES * C2_SLOT_BYTES + sizeof(float) * CH_MAX_LAYERS * 256 +
+                         8 * C2_N_BARRIERS + 16 + 128;
+    static bool configured2 = false;
+    if (!configured2) {
+      EP_CUDA_CHECK(cudaFuncSetAttribute(tc_chain2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      configured2 = true;
+    }
+    int clusters = ep::sm_count() / 2;
+    if (clusters > n_pairs) clusters = n_pairs;
+    b.trace = reinterpret_cast<unsigned long long*>(((uintptr_t)(uint32_t)ep::tune_flag(4) << 32) | (uint32_t)ep::tune_flag(3));
+    tc_chain2_kernel<MODE><<<2 * clusters, C2_THREADS, smem2, st>>>(b);
+    EP_LAUNCH_CHECK("tc_chain2_kernel");
+    return EP_OK;
+  }
   b.trace = reinterpret_cast<unsigned long long*>(((uintptr_t)(uint32_t)ep::tune_flag(4) << 32) | (uint32_t)ep::tune_flag(3));
   int grid = ep::sm_count();
   if (grid > n_pairs) grid = n_pairs;
@@ -856,7 +1270,7 @@ size_t ep_tc_packed_rows_bytes(int n, int d_padded) {
   return (size_t)n_tiles_for(n) * TILE_M * d_padded * 2;
 }
 
-size_t ep_tc_packed_weight_bytes(int out_padded, int in_padded) { return (size_t)out_padded * in_padded * 2; }
+size_t ep_tc_packed_weight_bytes(int out_padded, int in_padded) { return (size_t)W_REPLICAS * out_padded * in_padded * 2; }
 
 size_t ep_tc_relu_mask_bytes(int n, int d_padded) {
   if (n <= 0 || d_padded <= 0) return 0;
@@ -881,7 +1295,8 @@ int ep_tc_pack_weight_bf16(int out, int in, int out_padded, int in_padded, const
   EP_REQUIRE(out_padded % 8 == 0 && in_padded % 8 == 0 && W && Wp, "bad argument");
   const int total = out_padded * in_padded;
   pack_weight_kernel<<<ep::ceil_div(total, 256), 256, 0, ep::as_stream(stream)>>>(
-      out, in, out_padded, in_padded, W, static_cast<__nv_bfloat16*>(Wp), static_cast<__nv_bfloat16*>(WTp));
+      out, in, out_padded, in_padded, W, static_cast<__nv_bfloat16*>(Wp), static_cast<__nv_bfloat16*>(WTp),
+      out_padded % 32 == 0 && in_padded % 32 == 0);
   EP_LAUNCH_CHECK("pack_weight_kernel");
   return EP_OK;
 }

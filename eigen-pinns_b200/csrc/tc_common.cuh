@@ -40,6 +40,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   printf("eigenpinns_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
   __trap();
 }
+// for the one thread whose reaction time is on the critical path (the MMA issuer): poll with test_wait - try_wait
+// parks the thread in hardware and wakes it late when the shared-memory pipe is busy (~250 clk per wait measured)
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) return;
+  }
+  printf("eigenpinns_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+  __trap();
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {       // non-blocking
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -141,6 +165,20 @@ __device__ __forceinline__ uint32_t epi_block_fwd(const uint32_t (&v)[32], const
   uint32_t acc[4] = {0u, 0u, 0u, 0u};             // four independent chains instead of one 16-deep dependency chain
 #pragma unroll
   for (int i = 0; i < 16; ++i)                    // bit i <- lo half of w_i non-zero, bit 16 + i <- hi half
+    acc[i & 3] |= ((w[i] + 0x7FFF7FFFu) >> (15 - i)) & (0x00010001u << i);
+  return (acc[0] | acc[1]) | (acc[2] | acc[3]);
+}
+// the same with the bias read from shared memory where it is used (keeps 32 registers free for a second accumulator block)
+__device__ __forceinline__ uint32_t epi_block_fwd_sb(const uint32_t (&v)[32], const float* bias_smem, uint32_t (&w)[16]) {
+#pragma unroll
+  for (int g4 = 0; g4 < 8; ++g4) {
+    const float4 b = *reinterpret_cast<const float4*>(bias_smem + 4 * g4);
+    w[2 * g4] = pack_relu_bf16x2(__uint_as_float(v[4 * g4]) + b.x, __uint_as_float(v[4 * g4 + 1]) + b.y);
+    w[2 * g4 + 1] = pack_relu_bf16x2(__uint_as_float(v[4 * g4 + 2]) + b.z, __uint_as_float(v[4 * g4 + 3]) + b.w);
+  }
+  uint32_t acc[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
     acc[i & 3] |= ((w[i] + 0x7FFF7FFFu) >> (15 - i)) & (0x00010001u << i);
   return (acc[0] | acc[1]) | (acc[2] | acc[3]);
 }

@@ -222,7 +222,10 @@ EP_API size_t ep_tc_packed_weight_bytes(int out_padded, int in_padded);
 /* fp32 rows [n x d] -> packed bf16 tiles (corrector input h; gradient w.r.t. the network output). */
 EP_API int ep_tc_pack_rows_bf16(int n, int d, int d_padded, const float* X, int ldx, void* packed,
                          ep_stream_t stream);
-/* W fp32 [out x in] (nn.Linear layout) -> Wp [in_p/8][out_p][8] and, if WTp != NULL, WTp [out_p/8][in_p][8]. */
+/* W fp32 [out x in] (nn.Linear layout) -> Wp [in_p/8][out_p][8] and, if WTp != NULL, WTp [out_p/8][in_p][8].
+ * Each buffer holds TWO copies (ep_tc_packed_weight_bytes accounts for both): the layout above, then the same matrix
+ * as [K/32][half of N][4][N/2][8] - the order in which a CTA pair of the chain kernels (tcgen05 cta_group::2) streams
+ * its half of every K = 32 slab with one contiguous bulk copy. */
 EP_API int ep_tc_pack_weight_bf16(int out, int in, int out_padded, int in_padded, const float* W, void* Wp,
                            void* WTp, ep_stream_t stream);
 /* hidden layer: out_packed = relu(A W^T + b) (relu must be 1); relu_mask_out (may be NULL) receives one bit per

@@ -164,10 +164,23 @@ def test_bf16_training_tracks_reference():
 @pytest.mark.parametrize("n,dims", [(1, [32, 128, 16]), (129, [50, 128, 16]), (777, [82, 256, 256, 32]),
                                     (2500, [146, 256, 256, 256, 64]), (300, [25, 64, 64, 64, 16]),
                                     (128 * 149 * 2 + 5, [82, 256, 128, 256, 10]),
-                                    (40000, [82, 256, 256, 256, 256, 256, 256, 32])])
-def test_chain_kernels_equal_layerwise(n, dims):
+                                    (40000, [82, 256, 256, 256, 256, 256, 256, 32]),
+                                    (128 * (74 * 6 + 37) + 77, [82, 256, 256, 256, 32])])
+@pytest.mark.parametrize("pair_kernel", [True, False])
+def test_chain_kernels_equal_layerwise(n, dims, pair_kernel):
     """The fused all-layer kernels (ep_tc_chain_fwd_bf16 / ep_tc_chain_dx_bf16) must reproduce the layer-by-layer
-    kernels BIT FOR BIT: same bf16 roundings, same K order of the fp32 accumulation in TMEM."""
+    kernels BIT FOR BIT: same bf16 roundings, same K order of the fp32 accumulation in TMEM.  Both implementations:
+    tc_chain2_kernel (CTA pairs, tcgen05 cta_group::2: the default) and tc_chain_kernel (one CTA per tile pair,
+    ep_tune_set(6, 1)).  Sizes cover one row, ragged tiles, an odd tile count (a pair whose second CTA has no tile), odd
+    unit counts per cluster (a ping-pong step with one slot), several steps per cluster, layers of one weight slab."""
+    pkg("_cabi").call("ep_tune_set", 6, 0 if pair_kernel else 1)
+    try:
+        _chain_equals_layerwise(n, dims)
+    finally:
+        pkg("_cabi").call("ep_tune_set", 6, 0)
+
+
+def _chain_equals_layerwise(n, dims):
     engine, tcm = pkg("engine"), pkg("mlp_tc")
     g = torch.Generator().manual_seed(n)
     Ws = [torch.randn(dims[i + 1], dims[i], generator=g) / np.sqrt(dims[i]) for i in range(len(dims) - 1)]
