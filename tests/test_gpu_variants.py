@@ -71,9 +71,11 @@ def test_whitened_subspace_loss_value_and_gradient(k):
     rloss, rterms, reigs = vp.whitened_subspace_loss(Ur, Kt, Mt, lambda_orth=0.1)
     rloss.backward()
     assert abs(loss.item() - rloss.item()) <= 1e-5 * abs(rloss.item())
+    hinge_atol = 1e-5 * reigs.abs().max().item()     # the gap / ordering hinges act on DIFFERENCES of the estimates
     for name in ("zero", "trace", "diversity", "offdiag", "ordering", "stability"):
-        assert abs(terms[name].item() - rterms[name].item()) <= 1e-5 * abs(rterms[name].item()) + 1e-12, name
-    assert terms["orth"].item() < 1e-20 and rterms["orth"].item() < 1e-20       # ~0 by construction on both sides
+        atol = hinge_atol if name in ("diversity", "ordering") else 1e-12
+        assert abs(terms[name].item() - rterms[name].item()) <= 1e-5 * abs(rterms[name].item()) + atol, name
+    assert terms["orth"].item() < 1e-12 and rterms["orth"].item() < 1e-12       # rounding only: W B W = I by construction
     assert _rel(eigs.detach().cpu(), reigs.detach()) < 1e-5
     assert _rel(U.grad.cpu(), Ur.grad) < 1e-4
 
