@@ -112,6 +112,21 @@ class SimpleCorrector(nn.Module):
         return _run_net(self.net, self.corrector_input(x, edge_index), self.training)
 
 
+class AdaptiveCorrector(SimpleCorrector):
+    """Notebook variant with learnable per-mode scales (`AdaptiveCorrector` of
+    delta_pinns_validation/multigrid_gnn_refine_fixed.ipynb cell 4): correction = net([x, mean_nbr x]) * mode_scales.
+    Runs on the same kernels through autograd (aggregation, fused Linear+ReLU GEMMs); the scales are a torch parameter.
+    The fused TrainStepEngine does not carry the extra parameter and refuses this model - train it with the
+    autograd-capable methods (`_forward_pass`, `_compute_residual_ortho_loss`, variants.smoothness_loss)."""
+
+    def __init__(self, in_dim, out_dim, hidden_layers=(128, 64, 32), dropout=0.0, init_scale=0.01):
+        super().__init__(in_dim, out_dim, list(hidden_layers), dropout)
+        self.mode_scales = nn.Parameter(torch.ones(out_dim) * init_scale)
+
+    def forward(self, x, edge_index):
+        return super().forward(x, edge_index) * self.mode_scales.unsqueeze(0)
+
+
 class SpectralCorrector(nn.Module):
     def __init__(self, in_dim: int, out_dim: int, hidden_layers: List[int], dropout: float):
         super().__init__()

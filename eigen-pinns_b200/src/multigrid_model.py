@@ -172,6 +172,9 @@ class MultigridGNN:
                      optimizer):
         if self.dropout and self.dropout > 0.0:
             raise NotImplementedError("the fused training step supports dropout = 0.0 (the reference default)")
+        if hasattr(self.model, "mode_scales"):
+            raise NotImplementedError("the fused training step has no per-mode scale parameter (AdaptiveCorrector): "
+                                      "train it through the autograd-capable methods instead")
         x_feats = self._dev_f32(x_feats)
         if self.model_type == 'simple':
             h = self.model.corrector_input(x_feats, edge_index.to(self.device))

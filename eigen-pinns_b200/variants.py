@@ -12,6 +12,9 @@ the C ABI and writes each notebook's functional on top of them with torch for th
                            whitened Rayleigh matrix (zero mode, trace, gap hinge, off-diagonal, ordering, conditioning)
   single_mode_loss         delta_pinns_validation/iterative_eigenvalues_on_cloud.ipynb cell 1: one eigenfunction at a
                            time with a learnable eigenvalue, normalisation and deflation against earlier modes
+  smoothness_loss          delta_pinns_validation/multigrid_gnn_refine_fixed.ipynb cell 4 `train_gnn`: Laplacian energy of
+                           the correction and of the prediction (the per-mode scales of its AdaptiveCorrector live in
+                           src/corrector_model.py)
   CoordinateMLP            the coordinate networks of the first two (x in R^3 -> U in R^k, SiLU)
   EigenfunctionNN          the network of the third (sin activations, lambda = |w| appended to every layer's input)
 
@@ -151,6 +154,17 @@ def single_mode_loss(u, eigenvalue, pair: OperatorPair, previous=(), ortho_weigh
         Mp = ops.spmm(pair.M, u_prev.detach().reshape(-1, 1).contiguous()).squeeze(1)
         ortho = ortho + torch.dot(uf, Mp) ** 2
     return eig + norm + ortho_weight * ortho, eig, norm, ortho
+
+
+def smoothness_loss(corr, U_pred, pair: OperatorPair, denom=None):
+    """delta_pinns_validation/multigrid_gnn_refine_fixed.ipynb cell 4 (`train_gnn` loop body):
+        L_smooth_corr = sum(corr * (L corr)) / denom_res,  L_smooth_total = sum(U_pred * (L U_pred)) / denom_res
+    with denom_res = n * n_modes.  Returns (L_smooth_corr, L_smooth_total); the notebook adds w_smooth * (both)."""
+    n, k = U_pred.shape
+    denom = float(n * k) if denom is None else float(denom)
+    L_corr = ops.spmm_autograd(pair.K, corr)
+    Lu = ops.spmm_autograd(pair.K, U_pred)
+    return (corr * L_corr).sum() / denom, (U_pred * Lu).sum() / denom
 
 
 # ------------------------------------------------------------------------------------- networks

@@ -12,6 +12,8 @@ from the cells cited per function and the CUDA path is compared with this restat
                              scaling) from the same cell
     single_mode_loss         /root/reference/delta_pinns_validation/iterative_eigenvalues_on_cloud.ipynb cell 1
                              (compute_eigenvalue_loss, compute_normalization_loss, compute_orthogonality_loss)
+    smoothness_loss, AdaptiveCorrector   /root/reference/delta_pinns_validation/multigrid_gnn_refine_fixed.ipynb cell 4
+                             (`train_gnn` loop body: L_corr, L_smooth_corr, L_smooth_total; class AdaptiveCorrector)
     CoordinateMLP, EigenfunctionNN   the `MLP` / `EigenfunctionNN` classes of the same cells
 """
 import numpy as np
@@ -80,6 +82,31 @@ def single_mode_loss(u, eigenvalue, L, M, previous=(), ortho_weight=1.0):
     for u_prev in previous:
         ortho = ortho + torch.dot(u_flat, torch.sparse.mm(M, u_prev.reshape(-1, 1)).squeeze()) ** 2
     return eig + norm + ortho_weight * ortho, eig, norm, ortho
+
+
+def smoothness_loss(corr, U_pred, L, denom=None):
+    n, k = U_pred.shape
+    denom = float(n * k) if denom is None else float(denom)
+    return torch.sum(corr * torch.sparse.mm(L, corr)) / denom, torch.sum(U_pred * torch.sparse.mm(L, U_pred)) / denom
+
+
+class AdaptiveCorrector(nn.Module):
+    def __init__(self, in_dim, out_dim, hidden_sizes=(128, 64, 32), init_scale=0.01):
+        super().__init__()
+        layers, prev = [], in_dim * 2
+        for h in hidden_sizes:
+            layers += [nn.Linear(prev, h), nn.ReLU()]
+            prev = h
+        layers.append(nn.Linear(prev, out_dim))
+        self.net = nn.Sequential(*layers)
+        self.mode_scales = nn.Parameter(torch.ones(out_dim) * init_scale)
+
+    def forward(self, x, edge_index):
+        row, col = edge_index
+        agg = torch.zeros_like(x)
+        agg.index_add_(0, row, x[col])
+        deg = torch.bincount(row, minlength=x.shape[0]).unsqueeze(1).to(x.dtype).clamp(min=1.0)
+        return self.net(torch.cat([x, agg / deg], dim=1)) * self.mode_scales.unsqueeze(0)
 
 
 class Sin(nn.Module):

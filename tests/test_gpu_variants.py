@@ -9,7 +9,7 @@ import pytest
 import scipy.linalg
 import torch
 
-from gpu_util import pkg, dev, bunny_levels
+from gpu_util import pkg, dev, dropin, bunny_levels
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -140,3 +140,33 @@ def test_coordinate_mlp_trains_towards_the_low_modes():
         first = loss.item() if first is None else first
     assert loss.item() < 0.5 * first
     assert eigs.detach().sum().item() >= exact.sum() * (1 - 1e-4)      # Rayleigh-Ritz estimates bound from above
+
+
+def test_adaptive_corrector_and_smoothness_terms():
+    """AdaptiveCorrector (per-mode scales) + the two Laplacian-energy terms: forward, loss values and every parameter
+    gradient (including mode_scales) against the fp64 restatement."""
+    v = pkg("variants")
+    cm = dropin("corrector_model")
+    verts, K, M, _ = _setup(1, coarse=True)
+    n, k, d = K.shape[0], 8, 5
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    ei = np.stack([np.repeat(np.arange(n), 6), rng.integers(0, n, 6 * n)]).astype(np.int64)
+    U_base = (rng.standard_normal((n, k)) / np.sqrt(n)).astype(np.float32)
+    torch.manual_seed(2)
+    ref = vp.AdaptiveCorrector(d, k, (32, 16), init_scale=0.05).double()
+    net = cm.AdaptiveCorrector(d, k, (32, 16), 0.0, init_scale=0.05).to(dev())
+    net.load_state_dict({k_: t.float() for k_, t in ref.state_dict().items()})
+    pair = pkg("sparse").OperatorPair(K, M, dev())
+    corr = net(torch.from_numpy(x).to(dev()), torch.from_numpy(ei).to(dev()))
+    U_pred = torch.from_numpy(U_base).to(dev()) + corr
+    a, b = v.smoothness_loss(corr, U_pred, pair)
+    (3.0 * (a + b)).backward()
+    rcorr = ref(torch.from_numpy(x).double(), torch.from_numpy(ei))
+    rU = torch.from_numpy(U_base).double() + rcorr
+    ra, rb = vp.smoothness_loss(rcorr, rU, vp.to_torch_sparse(sp_f32(K)))
+    (3.0 * (ra + rb)).backward()
+    assert _rel(corr.detach().cpu(), rcorr.detach()) < 1e-5
+    assert abs(a.item() - ra.item()) <= 1e-5 * abs(ra.item()) and abs(b.item() - rb.item()) <= 1e-5 * abs(rb.item())
+    for (name, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+        assert _rel(p.grad.cpu(), q.grad) < 1e-4, name
