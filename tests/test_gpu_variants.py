@@ -168,5 +168,9 @@ def test_adaptive_corrector_and_smoothness_terms():
     (3.0 * (ra + rb)).backward()
     assert _rel(corr.detach().cpu(), rcorr.detach()) < 1e-5
     assert abs(a.item() - ra.item()) <= 1e-5 * abs(ra.item()) and abs(b.item() - rb.item()) <= 1e-5 * abs(rb.item())
+    scale = max(q.grad.abs().max().item() for q in ref.parameters())
     for (name, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
-        assert _rel(p.grad.cpu(), q.grad) < 1e-4, name
+        # (the gradient of the last bias is zero in exact arithmetic - constants are in the null space of L - and
+        #  rounding noise on both sides: hence the absolute part of the tolerance)
+        err = (p.grad.cpu().double() - q.grad).abs().max().item()
+        assert err <= 1e-4 * q.grad.abs().max().item() + 1e-6 * scale, name
