@@ -84,12 +84,14 @@ def test_torus_1m_k64_matches_oracle():
 def test_one_pass_residual_near_convergence():
     """U = exact generalised eigenvectors + 1e-4 of higher modes: the residual is ~1e-4 of |KU|, so the expansion
     sKK - 2 lam sKM + lam^2 sMM cancels ~8 digits.  fp64 accumulation keeps the loss within 1e-8 of an fp64
-    evaluation of sum (KU - lam MU)^2 on the same KU, MU, and within 1e-4 of the exact-arithmetic value."""
+    evaluation of sum (KU - lam MU)^2 on the same KU, MU; against the exact-arithmetic value the only error left is
+    the fp32 rounding of the SpMM outputs themselves (6e-8 of |KU| against a residual of 1e-4 |KU|: a few 1e-4
+    relative on the squared residual; 1.7e-4 and 0.6e-4 were measured for two start vectors of eigsh)."""
     from scipy.sparse.linalg import eigsh
     ops, sparse = pkg("ops"), pkg("sparse")
     fem, (K, M), _ = bunny_levels()
     n, k = K.shape[0], 16
-    vals, vecs = eigsh(K.tocsc(), k=k + 8, M=M.tocsc(), sigma=-0.01, which="LM")
+    vals, vecs = eigsh(K.tocsc(), k=k + 8, M=M.tocsc(), sigma=-0.01, which="LM", v0=np.ones(K.shape[0]))
     order = np.argsort(vals)
     vecs = vecs[:, order]
     rng = np.random.default_rng(3)
@@ -112,7 +114,7 @@ def test_one_pass_residual_near_convergence():
     KUx, MUx = K32 @ Ud, M32 @ Ud
     lamx = (Ud * KUx).sum(0) / ((Ud * MUx).sum(0) + 1e-12)
     ref_b = 1000.0 * ((KUx - MUx * lamx[None, :]) ** 2).mean()
-    assert got_res == pytest.approx(ref_b, rel=1e-4)
+    assert got_res == pytest.approx(ref_b, rel=1e-3)
     assert ref_b < 1e-6 * 1000.0 * (KUx ** 2).mean()          # the case really is near convergence
     # (c) the reference's own fp32 evaluation carries rounding noise of this order; ours is the more accurate one
     l_res, _, _ = step_port.residual_ortho_loss(U.cpu(), [K], [M], [0], 1000.0, 10.0, k)
