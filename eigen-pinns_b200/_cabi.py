@@ -75,6 +75,10 @@ SIGNATURES = {
     "ep_knn_grid_f64": (c_int, [c_i64, c_p, c_i64, c_p, c_p, c_p, c_p, c_d, c_p, c_int, c_p, c_p, c_p]),
     "ep_gather_rows_f32": (c_int, [c_int, c_int, c_p, c_p, c_int, c_p, c_int, c_p]),
     "ep_scatter_add_rows_f32": (c_int, [c_int, c_int, c_p, c_p, c_int, c_p, c_int, c_p]),
+    "ep_dist_nccl_version": (c_int, []),
+    "ep_halo_exchange_f32": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_int, c_p, c_int, c_p, c_p, c_p]),
+    "ep_allreduce_sum_f64": (c_int, [c_p, c_sz, c_p, c_p]),
+    "ep_allreduce_sum_f32": (c_int, [c_p, c_sz, c_p, c_p]),
 }
 
 
@@ -93,6 +97,7 @@ KERNELS_PER_CALL = {
     "ep_voxel_select_f64": 6, "ep_gather_rows_f32": 1, "ep_knn_grid_f64": 1, "ep_fem_elements_f64": 1, "ep_fem_segment_sum_f64": 1, "ep_scatter_add_rows_f32": 1,
     "ep_tc_pack_rows_bf16": 1, "ep_tc_pack_weight_bf16": 1, "ep_tc_linear_fwd_bf16": 1, "ep_tc_linear_final_bf16": 1,
     "ep_tc_linear_dx_bf16": 1, "ep_tc_linear_dw_bf16": 2, "ep_tc_chain_fwd_bf16": 1, "ep_tc_chain_dx_bf16": 1,
+    "ep_halo_exchange_f32": 1,
 }
 launch_counter = 0
 launch_by_entry = {}          # entry point -> kernels launched through it (bench.py reports the per-step table)

@@ -11,6 +11,8 @@ Row space of a rank, per level:  [owned rows | halo rows].  The corrector MLP si
 rows too (zero input features, result overwritten by the exchange), so every kernel of the single-GPU
 engine is reused unchanged on rank-local CSR blocks whose columns index that row space.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -19,6 +21,87 @@ from . import ops
 from .engine import TrainStepEngine, FlatParams, StepConfig
 from .partition import LevelPlan
 from .sparse import OperatorPair
+
+
+def nccl_comm_ptr(group=None):
+    """ncclComm_t of this rank in `group` as an integer (what the C ABI's multi-GPU entry points take), or None when
+    the group is not an NCCL group of this torch build.  The communicator is created lazily by the first collective."""
+    try:
+        pg = group if group is not None else dist.distributed_c10d._get_default_group()
+        backend = pg._get_backend(torch.device("cuda", torch.cuda.current_device()))
+        ptr = backend._comm_ptr()
+        return int(ptr) if ptr else None
+    except Exception:
+        return None
+
+
+class _StreamWork:
+    """wait() makes the current stream wait for what was enqueued on the side stream (mirrors dist.Work.wait)."""
+
+    def __init__(self, event):
+        self.event = event
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.event)
+
+
+class CabiHaloExchanger:
+    """The same exchange through the C ABI (`ep_halo_exchange_f32`: gather kernel + one NCCL group of sends / receives on
+    a side stream) instead of torch.distributed's batch_isend_irecv - the path a non-Python host takes.  Selected with
+    EP_HALO_CABI=1; results are identical (tests/multi_gpu_check.py, mode `cabi`)."""
+
+    def __init__(self, plan: LevelPlan, device, group=None):
+        import ctypes
+        self.plan, self.group = plan, group
+        peers = sorted(set(plan.send) | set(plan.recv))
+        send_off, recv_off, idx = [0], [0], []
+        for p in peers:
+            ix = plan.send.get(p, np.zeros(0, np.int64))
+            idx.append(np.asarray(ix, dtype=np.int32))
+            send_off.append(send_off[-1] + len(ix))
+        # the halo block is laid out peer by peer in ascending peer order (partition.LevelPlan.recv: peer -> (off, cnt))
+        for p in peers:
+            off, cnt = plan.recv.get(p, (recv_off[-1], 0))
+            assert cnt == 0 or off == recv_off[-1], "halo blocks must be contiguous in peer order"
+            recv_off.append(recv_off[-1] + cnt)
+        arr = lambda v: (ctypes.c_int * len(v))(*[int(x) for x in v])
+        self.n_peers = len(peers)
+        self._peers, self._send_off, self._recv_off = arr(peers), arr(send_off), arr(recv_off)
+        self.send_idx = torch.from_numpy(np.concatenate(idx) if idx else np.zeros(0, np.int32)).to(device)
+        self.n_send = send_off[-1]
+        self._bufs = {}
+        self.stream = torch.cuda.Stream(device=device)
+        self._comm = None
+
+    def start(self, rows, n_own):
+        import ctypes
+        from . import _cabi
+        if self.n_peers == 0:
+            return []
+        if self._comm is None:
+            self._comm = nccl_comm_ptr(self.group)
+            if self._comm is None:
+                raise _cabi.EpError("EP_HALO_CABI=1 needs an initialised NCCL process group (run one collective first)")
+        k = rows.shape[1]
+        assert rows.is_contiguous() and rows.dtype == torch.float32
+        if k not in self._bufs:
+            self._bufs[k] = torch.empty((max(self.n_send, 1), k), dtype=torch.float32, device=rows.device)
+        ready = torch.cuda.Event()
+        ready.record()
+        self.stream.wait_event(ready)
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        with torch.cuda.stream(self.stream):
+            _cabi.call("ep_halo_exchange_f32", ctypes.c_void_p(self._comm), self.n_peers, self._peers, self._send_off,
+                       P(self.send_idx), self._recv_off, k, P(rows), k, P(self._bufs[k]),
+                       ctypes.c_void_p(rows.data_ptr() + n_own * k * 4), ctypes.c_void_p(self.stream.cuda_stream))
+        done = torch.cuda.Event()
+        done.record(self.stream)
+        return [_StreamWork(done)]
+
+    def exchange(self, rows, n_own):
+        for w in self.start(rows, n_own):
+            w.wait()
+        return rows
 
 
 class HaloExchanger:
@@ -84,7 +167,10 @@ class ShardedTrainStepEngine(TrainStepEngine):
             off += pl.n_own + pl.n_halo
         assert off == h_local.shape[0] == U_base_local.shape[0]
         super().__init__(h_local, U_base_local, pairs, offsets, params, cfg, lam_target, mlp_mode)
-        self.halo = [HaloExchanger(pl, dev, lambda rows, idx, out: ops.gather_rows(rows, idx, out=out), group) for pl in plans]
+        if os.environ.get("EP_HALO_CABI") == "1":
+            self.halo = [CabiHaloExchanger(pl, dev, group) for pl in plans]
+        else:
+            self.halo = [HaloExchanger(pl, dev, lambda rows, idx, out: ops.gather_rows(rows, idx, out=out), group) for pl in plans]
         self.overlap = True                     # interior rows while the halo is in flight
         self._grad_work = []
         # Seven small all-reduces interleaved with the backward only pay when the kernels they hide behind are long:

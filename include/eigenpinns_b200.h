@@ -345,6 +345,26 @@ EP_API int ep_gather_rows_f32(int n_idx, int k, const int32_t* idx, const float*
 EP_API int ep_scatter_add_rows_f32(int n_idx, int k, const int32_t* idx, const float* src, int lds,
                             float* dst, int ldd, ep_stream_t stream);
 
+/* ---- multi-GPU: the exchanges of the vertex-sharded step, for hosts that do not go through torch.distributed ----
+ * The reference has no distributed code; these are the communication steps the sharded path adds around
+ * src/multigrid_model.py:301-324.  `nccl_comm` is the caller's ncclComm_t (one rank per GPU).  NCCL is not
+ * linked: its entry points are resolved at run time from the libnccl.so.2 the process already uses, so the
+ * communicator and the calls always belong to the same NCCL instance.  Everything is enqueued on `stream`; run the
+ * exchange on a side stream to overlap it with the interior rows (what dist_engine.py does).
+ *
+ * ep_halo_exchange_f32: row space of a rank = [owned rows | halo rows], `rows` points at the owned block and
+ * `halo_rows` at the halo block of the same dense (ld == k) array.  For peer p (rank peer_rank[p]) the owned rows
+ * send_idx[send_offset[p] .. send_offset[p+1]) (device int32) are packed into send_buf (device, send_offset[n_peers] x k)
+ * and sent, and recv_offset[p+1] - recv_offset[p] rows are received into halo_rows + recv_offset[p] * k, all in one
+ * NCCL group.  The three offset / rank arrays are host arrays of n_peers (+1) entries. */
+EP_API int ep_dist_nccl_version(void);        /* 0: no NCCL library could be resolved in this process */
+EP_API int ep_halo_exchange_f32(void* nccl_comm, int n_peers, const int* peer_rank, const int* send_offset,
+                         const int32_t* send_idx, const int* recv_offset, int k, const float* rows, int ld,
+                         float* send_buf, float* halo_rows, ep_stream_t stream);
+/* in-place sum over all ranks: the packed fp64 partials of a level / the flat fp32 gradient buffer. */
+EP_API int ep_allreduce_sum_f64(void* nccl_comm, size_t count, double* buf, ep_stream_t stream);
+EP_API int ep_allreduce_sum_f32(void* nccl_comm, size_t count, float* buf, ep_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

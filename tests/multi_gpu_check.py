@@ -21,6 +21,14 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     if mode.startswith("torus"):
         return torus_check(mode, rank, world, dev)
+    label = mode
+    cabi_ok = True
+    if mode == "cabi":
+        # the multi-GPU entry points of the C ABI (ep_halo_exchange_f32, ep_allreduce_sum_*) on torch's communicator:
+        # all-reduces against torch.distributed, then the whole sharded step with the C-ABI halo exchange
+        cabi_ok = cabi_allreduce_check(rank, world, dev)
+        os.environ["EP_HALO_CABI"] = "1"
+        mode = "fp32"
     import bench
     import config as cfg_mod
     import multigrid_model
@@ -41,6 +49,8 @@ def main():
         opt, _ = gnn._create_optimizer(gnn.lr, gnn.weight_decay)
         if sharded:
             eng = de.make_sharded_engine(gnn, x_feats, edge_all, U_norm[0], w["K"], w["M"], lam0, opt, rank, world)
+            if label == "cabi":
+                cabi_ok = cabi_ok and type(eng.halo[0]).__name__ == "CabiHaloExchanger"
         else:
             eng = gnn._make_engine(x_feats, edge_all, A_norm, U_norm[0], [w["K"]], [w["M"]], lam0, [0], opt)
         losses = [eng.step(2500 + i).cpu().numpy().copy() for i in range(2)]
@@ -54,13 +64,36 @@ def main():
     ok = np.allclose(l1, l2, rtol=tol, atol=1e-9)
     perr = (p1 - p2).abs().max().item()
     ok = ok and perr <= (2e-5 if mode == "fp32" else 2e-3)
-    ok = ok and torch.allclose(lam1[0], lam2[0], rtol=tol, atol=1e-6)
+    ok = ok and torch.allclose(lam1[0], lam2[0], rtol=tol, atol=1e-6) and cabi_ok
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("MULTI_GPU_CHECK", "OK" if flag.item() == 1.0 else "FAIL", "world", world, "mode", mode,
+        print("MULTI_GPU_CHECK", "OK" if flag.item() == 1.0 else "FAIL", "world", world, "mode", label,
               "loss_single", l1[:, 5].tolist(), "loss_sharded", l2[:, 5].tolist(), "param_err", perr)
     _leave(flag.item() == 1.0)
+
+
+def cabi_allreduce_check(rank, world, dev):
+    import ctypes
+    cabi = importlib.import_module("eigen-pinns_b200._cabi")
+    de = importlib.import_module("eigen-pinns_b200.dist_engine")
+    warm = torch.ones(1, device=dev)
+    dist.all_reduce(warm)                                   # creates the communicator
+    comm = de.nccl_comm_ptr()
+    if comm is None or cabi.query("ep_dist_nccl_version") == 0:
+        return False
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    ok = True
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for dtype, entry in ((torch.float64, "ep_allreduce_sum_f64"), (torch.float32, "ep_allreduce_sum_f32")):
+        for count in (1, 1109, 362_529):
+            a = torch.randn(count, device=dev, dtype=dtype, generator=g)
+            b = a.clone()
+            dist.all_reduce(a)
+            cabi.call(entry, ctypes.c_void_p(comm), count, ctypes.c_void_p(b.data_ptr()), st)
+            torch.cuda.synchronize()
+            ok = ok and torch.allclose(a, b, rtol=1e-12 if dtype == torch.float64 else 1e-5, atol=1e-12 if dtype == torch.float64 else 1e-6)
+    return ok
 
 
 def _leave(ok):

@@ -22,7 +22,7 @@ def _worlds():
 
 
 @pytest.mark.parametrize("mode,launch", [("fp32", "eager"), ("bf16", "eager"), ("bf16", "graph"), ("torus_fp32", "eager"),
-                                         ("torus_bf16", "eager")])
+                                         ("torus_bf16", "eager"), ("cabi", "eager"), ("cabi", "graph")])
 def test_sharded_engine_matches_single_gpu(mode, launch):
     worlds = _worlds()
     if not worlds:
