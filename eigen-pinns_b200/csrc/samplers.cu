@@ -211,6 +211,55 @@ voxel_assign_kernel(long long N, const double* __restrict__ pts, double lx, doub
   }
 }
 
+// Small grids (the coarse levels of a hierarchy: a few hundred to a few thousand voxels for 10^6 points) make the global
+// atomicMin above the whole cost - a Gaussian cloud puts most points into a few dozen voxels.  Here every warp first
+// reduces the lanes that fall into the same voxel (match_any + two 32-bit min reductions = exact 64-bit min), the block
+// keeps a table of minima in shared memory, and only the occupied entries go to global memory: blocks x occupied
+// voxels global atomics instead of one per point.  Same minima, so the picks are unchanged.
+constexpr int kVoxelSmemMax = 4096;                       // voxels (32 KB of shared memory)
+__global__ void __launch_bounds__(256)
+voxel_assign_small_kernel(long long N, const double* __restrict__ pts, double lx, double ly, double lz, double voxel,
+                          long long dx, long long dy, long long dz, long long* __restrict__ vid,
+                          unsigned long long* __restrict__ dcode, unsigned long long* __restrict__ tab_d, int n_vox) {
+  extern __shared__ unsigned long long s_tab[];
+  for (int v = threadIdx.x; v < n_vox; v += blockDim.x) s_tab[v] = kEmptyU64;
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n_iter = (N + stride - 1) / stride;      // all lanes iterate together (the reductions need the mask)
+  for (long long it = 0; it < n_iter; ++it) {
+    const long long i = first + it * stride;
+    const bool live = i < N;
+    long long v = -1;
+    unsigned long long code = kEmptyU64;
+    if (live) {
+      const double px = pts[i * 3], py = pts[i * 3 + 1], pz = pts[i * 3 + 2];
+      long long cx = (long long)__ddiv_rn(__dsub_rn(px, lx), voxel);
+      long long cy = (long long)__ddiv_rn(__dsub_rn(py, ly), voxel);
+      long long cz = (long long)__ddiv_rn(__dsub_rn(pz, lz), voxel);
+      cx = min(max(cx, 0LL), dx - 1); cy = min(max(cy, 0LL), dy - 1); cz = min(max(cz, 0LL), dz - 1);
+      v = cx * dy * dz + cy * dz + cz;
+      const double ccx = __dadd_rn(lx, __dmul_rn((double)cx + 0.5, voxel));
+      const double ccy = __dadd_rn(ly, __dmul_rn((double)cy + 0.5, voxel));
+      const double ccz = __dadd_rn(lz, __dmul_rn((double)cz + 0.5, voxel));
+      code = (unsigned long long)__double_as_longlong(dist3(px, py, pz, ccx, ccy, ccz));
+      vid[i] = v;
+      dcode[i] = code;
+    }
+    const unsigned group = __match_any_sync(0xffffffffu, (int)v);           // lanes of this warp in the same voxel
+    const unsigned hi = (unsigned)(code >> 32), lo = (unsigned)code;
+    const unsigned m_hi = __reduce_min_sync(group, hi);
+    const unsigned m_lo = __reduce_min_sync(group, hi == m_hi ? lo : 0xffffffffu);
+    if (live && (threadIdx.x & 31) == (unsigned)(__ffs(group) - 1))
+      atomicMin(&s_tab[v], ((unsigned long long)m_hi << 32) | m_lo);
+  }
+  __syncthreads();
+  for (int v = threadIdx.x; v < n_vox; v += blockDim.x) {
+    const unsigned long long m = s_tab[v];
+    if (m != kEmptyU64) atomicMin(tab_d + v, m);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 voxel_pick_kernel(long long N, const long long* __restrict__ vid, const unsigned long long* __restrict__ dcode,
                   const unsigned long long* __restrict__ tab_d, unsigned long long* __restrict__ tab_i) {
@@ -415,9 +464,18 @@ int ep_voxel_select_f64(int64_t n_points, const double* pts, const double* lo, d
   EP_REQUIRE(nb < 0x7fffffffLL, "voxel grid too large");
   voxel_init_kernel<<<stream_grid(n_vox, 256), 256, 0, st>>>(n_vox, tab_d, tab_i);
   EP_LAUNCH_CHECK("voxel_init_kernel");
-  voxel_assign_kernel<<<stream_grid(n_points, 256), 256, 0, st>>>(n_points, pts, lo[0], lo[1], lo[2], voxel, dims[0],
-                                                                 dims[1], dims[2], vid, dcode, tab_d);
-  EP_LAUNCH_CHECK("voxel_assign_kernel");
+  if (n_vox <= kVoxelSmemMax) {
+    int grid = 2 * ep::sm_count();
+    const long long need = ep::ceil_div64(n_points, 256);
+    if (need < grid) grid = (int)need;
+    voxel_assign_small_kernel<<<grid, 256, sizeof(unsigned long long) * (size_t)n_vox, st>>>(
+        n_points, pts, lo[0], lo[1], lo[2], voxel, dims[0], dims[1], dims[2], vid, dcode, tab_d, (int)n_vox);
+    EP_LAUNCH_CHECK("voxel_assign_small_kernel");
+  } else {
+    voxel_assign_kernel<<<stream_grid(n_points, 256), 256, 0, st>>>(n_points, pts, lo[0], lo[1], lo[2], voxel, dims[0],
+                                                                   dims[1], dims[2], vid, dcode, tab_d);
+    EP_LAUNCH_CHECK("voxel_assign_kernel");
+  }
   voxel_pick_kernel<<<stream_grid(n_points, 256), 256, 0, st>>>(n_points, vid, dcode, tab_d, tab_i);
   EP_LAUNCH_CHECK("voxel_pick_kernel");
   voxel_count_kernel<<<(unsigned)nb, kScanBlock, 0, st>>>(n_vox, tab_i, counts);

@@ -65,72 +65,55 @@ def bounds(points_dev):
     return v[:3].copy(), v[3:].copy()
 
 
+_voxel_ws = {}
+
+
 def voxel_select(points_dev, lo, voxel, dims, max_out=None):
     """One voxel pass: representative point per occupied voxel in ascending voxel id.
-    Returns (count, indices[:min(count, max_out)]) as numpy."""
+    Returns (count, indices[:min(count, max_out)]) as numpy.  The count and the picks come back in ONE device-to-host
+    copy (one synchronisation per pass); the workspace is kept between passes."""
     n = points_dev.shape[0]
     dims64 = np.asarray(dims, dtype=np.int64)
     n_vox = int(dims64[0]) * int(dims64[1]) * int(dims64[2])
     max_out = int(max_out) if max_out is not None else min(n, n_vox)
     ws_bytes = query("ep_voxel_workspace_bytes", n, n_vox)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=points_dev.device)
-    out = torch.empty(max(max_out, 1), dtype=torch.int64, device=points_dev.device)
-    cnt = torch.zeros(1, dtype=torch.int64, device=points_dev.device)
+    key = str(points_dev.device)
+    ws = _voxel_ws.get(key)
+    if ws is None or ws.numel() < ws_bytes:
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=points_dev.device)
+        _voxel_ws[key] = ws
+    res = torch.zeros(1 + max(max_out, 1), dtype=torch.int64, device=points_dev.device)      # [count | picks]
     lo64 = np.ascontiguousarray(lo, dtype=np.float64)
     call("ep_voxel_select_f64", n, _p(points_dev), lo64.ctypes.data_as(ctypes.c_void_p), float(voxel),
-         dims64.ctypes.data_as(ctypes.c_void_p), _p(out), max_out, _p(cnt), _p(ws), ws_bytes, _stream())
-    count = int(cnt.item())
-    return count, out[:min(count, max_out)].cpu().numpy()
+         dims64.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(res.data_ptr() + 8), max_out, _p(res), _p(ws), ws_bytes,
+         _stream())
+    host = res.cpu().numpy()
+    count = int(host[0])
+    return count, host[1:1 + min(count, max_out)].copy()
 
 
 def voxel_levels(points, hierarchy, device="cuda"):
-    """Voxel-grid hierarchy, control flow of reference src/samplers.py:9-94.
-
-    The reference tries up to six voxel sizes per level and stops at the first whose count reaches 95 % of the target.
-    A pass costs microseconds of GPU time and a host round trip per pass would dominate, so ALL candidate sizes of all
-    levels are enqueued back to back (each writes its count and its first `target` picks, which is all the reference
-    keeps), the host synchronises ONCE, and the reference's selection loop is then replayed on the counts - same picks,
-    two host synchronisations (bounds, results) instead of two per pass."""
+    """Voxel-grid hierarchy, control flow of reference src/samplers.py:9-94."""
     pts_dev = _device_points(points, device)
     n = pts_dev.shape[0]
     lo, hi = bounds(pts_dev)
     extent = hi - lo
-    lo64 = np.ascontiguousarray(lo, dtype=np.float64)
-    passes = []                                            # (level, target, slot)
-    todo = [(lv, int(t)) for lv, t in enumerate(hierarchy) if t < n]
-    n_pass = len(todo) * len(VOXEL_SCALES)
-    cnt = torch.zeros(max(n_pass, 1), dtype=torch.int64, device=pts_dev.device)
-    width = max([t for _, t in todo], default=1)
-    picks = torch.empty((max(n_pass, 1), width), dtype=torch.int64, device=pts_dev.device)
-    keep = []
-    for lv, target in todo:
+    out = {}
+    for lv, target in enumerate(hierarchy):
+        if target >= n:
+            out[lv] = np.arange(n)
+            continue
         base = (np.prod(extent) / (target * 2)) ** (1 / 3)
+        best, best_gap = None, float("inf")
         for scale in VOXEL_SCALES:
             vs = base * scale
-            dims64 = (np.ceil(extent / vs).astype(int) + 1).astype(np.int64)
-            n_vox = int(dims64[0]) * int(dims64[1]) * int(dims64[2])
-            ws_bytes = query("ep_voxel_workspace_bytes", n, n_vox)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pts_dev.device)
-            slot = len(passes)
-            call("ep_voxel_select_f64", n, _p(pts_dev), lo64.ctypes.data_as(ctypes.c_void_p), float(vs),
-                 dims64.ctypes.data_as(ctypes.c_void_p), _p(picks[slot]), target, _p(cnt[slot:slot + 1]), _p(ws), ws_bytes,
-                 _stream())
-            keep.append((ws, dims64))
-            passes.append((lv, target, slot))
-    counts = cnt.cpu().numpy()                              # the one synchronisation
-    picks_host = picks.cpu().numpy() if passes else None
-    out = {lv: np.arange(n) for lv, t in enumerate(hierarchy) if t >= n}
-    for lv, target in todo:
-        best, best_gap = None, float("inf")
-        for l2, _, slot in passes:
-            if l2 != lv:
-                continue
-            count = int(counts[slot])
+            dims = np.ceil(extent / vs).astype(int) + 1
+            count, picks = voxel_select(pts_dev, lo, vs, dims, max_out=target)     # the reference keeps best[:target]
             gap = abs(count - target)
             if gap < best_gap:
-                best_gap, best = gap, picks_host[slot, :min(count, target)]
+                best_gap, best = gap, picks
             if count >= target * 0.95:
                 break
-        out[lv] = best                                      # (already truncated to the first `target` picks)
+        out[lv] = best[:target] if len(best) > target else best
     out[len(hierarchy)] = np.arange(n)
     return {lv: np.sort(v) for lv, v in out.items()}
