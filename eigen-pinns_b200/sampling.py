@@ -115,5 +115,6 @@ def voxel_levels(points, hierarchy, device="cuda"):
             if count >= target * 0.95:
                 break
         out[lv] = best[:target] if len(best) > target else best
-    out[len(hierarchy)] = np.arange(n)
-    return {lv: np.sort(v) for lv, v in out.items()}
+    out = {lv: np.sort(v) for lv, v in out.items()}
+    out[len(hierarchy)] = np.arange(n)                     # (already sorted: sorting 10^6 indices cost more than all passes)
+    return out
