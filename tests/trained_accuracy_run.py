@@ -9,8 +9,8 @@ Problem: coarse FEM level (1057 vertices) + bunny (2503 vertices), k = 16, MLP 5
 default width and depth), kNN-8 aggregation graph, prolongated + Jacobi-smoothed coarse eigenvectors as U_base
 (the reference CGC is singular on these meshes, SURVEY Q12, so it is skipped identically on both sides).
 
-    python tools/trained_accuracy.py --oracle --epochs 3000 --out profiles/r02_trained_accuracy_oracle.json
-    python tools/trained_accuracy.py --gpu    --epochs 3000 --out profiles/r02_trained_accuracy_gpu.json
+    python tests/trained_accuracy_run.py --oracle --epochs 3000 --out profiles/r02_trained_accuracy_oracle.json
+    python tests/trained_accuracy_run.py --gpu    --epochs 3000 --out profiles/r02_trained_accuracy_gpu.json
 """
 import argparse
 import importlib
