@@ -59,3 +59,15 @@ def test_networks_follow_the_notebook_shapes():
     u, lam = one(x)
     assert u.shape == (7, 1) and lam.item() == 2.5                # lambda = |w|
     assert one.fc2.weight.shape == (16, 17)                        # the eigenvalue is appended to every layer's input
+
+
+def test_operator_preparation_matches_the_restatement():
+    """variants.frobenius_normalised (product, sparse) == the notebook's dense preparation restated in the oracle."""
+    variants = importlib.import_module("eigen-pinns_b200.variants")
+    _, K, M = _coarse()
+    Kn, Mn, ks, ms = variants.frobenius_normalised(K, M, epsilon=1e-4)
+    rKn, rMn, rks, rms = vp.frobenius_normalised(K, M, epsilon=1e-4)
+    dense = K.toarray() + 1e-4 * np.eye(K.shape[0])
+    assert abs(ks - np.linalg.norm(dense, "fro")) < 1e-9 * ks and abs(ks - rks) < 1e-12 * ks and abs(ms - rms) < 1e-12 * ms
+    assert abs(Kn - rKn).max() < 1e-15 and abs(Mn - rMn).max() < 1e-15
+    assert abs(np.sqrt((Kn.toarray() ** 2).sum()) - 1.0) < 1e-12
