@@ -90,3 +90,34 @@ def test_multi_gpu_entry_points_resolve_nccl_at_run_time():
         cabi.call("ep_halo_exchange_f32", None, 1, None, None, None, None, 4, None, 4, None, None, None)
     cabi.call("ep_halo_exchange_f32", None, 0, None, None, None, None, 4, None, 4, None, None, None)   # no peers: no-op
     cabi.call("ep_allreduce_sum_f64", ctypes.c_void_p(1), 0, None, None)                                 # empty: no-op
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 (-pedantic) and as C++, and a C program links against the
+    shared library and calls it (no GPU needed for ep_version / the size queries)."""
+    import shutil
+    import subprocess
+    cabi = importlib.import_module("eigen-pinns_b200._cabi")
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "use_abi.c"
+    src.write_text('#include <stdio.h>\n#include "eigenpinns_b200.h"\n'
+                   'int main(void) {\n'
+                   '  if (ep_version() <= 0) return 1;\n'
+                   '  if (ep_eigen_partials_len(32) != 32 * 32 + 5 * 32) return 2;\n'
+                   '  if (ep_tc_pad_features(82, 0) != 96) return 3;\n'
+                   '  /* bad arguments are reported, not crashed on */\n'
+                   '  if (ep_spmm_csr_f32(-1, 4, 0, 0, 0, 0, 4, 0, 4, 0) == EP_OK) return 4;\n'
+                   '  if (ep_last_error_string() == 0) return 5;\n'
+                   '  printf("ok\\n");\n  return 0;\n}\n')
+    inc = os.path.join(ROOT, "include")
+    lib_dir = os.path.dirname(cabi.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-c", str(src), "-o",
+                    str(tmp_path / "a.o")], check=True)
+    subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", "-I", inc, "-x", "c++", "-c", str(src), "-o",
+                    str(tmp_path / "b.o")], check=True)
+    exe = tmp_path / "use_abi"
+    subprocess.run(["gcc", str(tmp_path / "a.o"), "-o", str(exe), "-L", lib_dir, "-leigenpinns_b200",
+                    "-Wl,-rpath," + lib_dir], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", (out.returncode, out.stdout, out.stderr)
